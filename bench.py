@@ -1,0 +1,232 @@
+#!/usr/bin/env python
+"""bench.py -- factor GFLOP/s & time (FP64, 3-D Laplacian) of the numeric sparse Cholesky path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lapl3d_7pt_128] [--impl reference]
+
+One "step" = one numeric factorization (assemble + level loop) of the workload.  `value` is algorithmic
+GFLOP/s (flops of the reference's BLAS call list / device time of the level loop, CUDA events on the
+launching stream, inputs resident in HBM); `e2e` is the same metric through the C-ABI call that takes
+HOST buffers (H2D of A's values, assemble, factor, D2H of diag(L) inside the timed region).
+`--impl reference` times the reference's algorithm on the host cores (CPU oracle over host OpenBLAS,
+the only place besides cpu_baseline where oracle/ is executed) on a bounded sample of the workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, nz, stencil, levels[0 = utils.py rule])
+    "lapl3d_7pt_128": (128, 128, 128, 7, 0),   # BASELINE config 4 (the headline)
+    "lapl3d_7pt_64": (64, 64, 64, 7, 0),       # config 3
+    "lapl2d_5pt_512": (512, 512, 1, 5, 0),     # config 2
+    "lapl3d_27pt_96": (96, 96, 96, 27, 0),     # config 5
+    "lapl3d_7pt_15": (15, 15, 15, 7, 5),       # config 1 grid (generated ordering)
+}
+# bounded CPU sample per workload: (grid, description)
+CPU_SAMPLE = {
+    "lapl3d_7pt_128": ((80, 80, 80, 7, 0), "80^3 7-pt Laplacian (a quarter of the 128^3 workload's unknowns, 1/17 of its "
+                                           "flops), full factorization, same generator"),
+    "lapl3d_7pt_64": ((48, 48, 48, 7, 0), "48^3 7-pt Laplacian, full factorization, same generator"),
+    "lapl2d_5pt_512": ((512, 512, 1, 5, 0), "the full 512x512 5-pt workload"),
+    "lapl3d_27pt_96": ((40, 40, 40, 27, 0), "40^3 27-pt Laplacian, full factorization, same generator"),
+    "lapl3d_7pt_15": ((15, 15, 15, 7, 5), "the full 15^3 workload"),
+}
+METRIC = "factor GFLOP/s (FP64, 3D Laplacian numeric sparse Cholesky)"
+
+
+def fp64_peak():
+    """FP64 peak in TFLOP/s.  MEASURED_PEAKS.json carries no FP64 figure, so the denominator is this
+    repo's own measurement on the pool's B200 (tools/fp64_peak.cu, summary in profiles/)."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["fp64_tflops"]), d.get("how", "profiles/fp64_peak.json")
+    return 37.0, "nominal HGX B200 FP64 (296 TF / 8 GPUs); no measurement committed yet"
+
+
+class ClockSampler:
+    def __init__(self):
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self, device=0):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) >= 9 and r[0] == str(device)]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_reference(workload, threads=None, repeats=1):
+    """the reference's blocked algorithm over host BLAS (oracle/), timed on this box's host cores"""
+    from cholesky_b200 import Cholesky
+    from oracle import oracle as orc
+    grid, desc = CPU_SAMPLE[workload]
+    threads = threads or os.cpu_count() or 1
+    tmp = tempfile.mkdtemp()
+    m, o, c = (os.path.join(tmp, x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    Cholesky().generate(*grid).write_inputs(m, o, c)   # input generation only; no numeric call
+    ref = orc.Oracle(m, o, c)
+    best = None
+    for _ in range(repeats):
+        s = ref.factor(threads=threads)
+        best = s if best is None else min(best, s)
+    return {"value": ref.flops() / best * 1e-9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+            "sample": desc + f"; {ref.flops():.4g} flops in {best:.2f} s; host BLAS {orc.blas_config()}",
+            "seconds": best}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("CHOL_BENCH_WORKLOAD", "lapl3d_7pt_128"))
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    grid = WORKLOADS[args.workload]
+    config = {"workload": f"{args.workload}: {grid[0]}x{grid[1]}x{grid[2]} grid, {grid[3]}-point Laplacian, geometric ND "
+                          f"(levels by utils.py rule), reference-format ord/clust generated in memory",
+              "l2_policy": "inputs larger than L2: every step re-assembles and rewrites the whole factor "
+                           "(>= 1.5 GB, 126 MB L2)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.time()
+        res = []
+        for _ in range(max(1, min(args.steps, 3))):
+            res.append(cpu_reference(args.workload))
+        best = max(res, key=lambda r: r["value"])
+        line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+                "steps": len(res), "warmup": 0, "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": best["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.time() - t0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cholesky_b200 import Cholesky
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the numeric path has no CPU fallback")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    ch = Cholesky(local_rank).generate(*grid)
+    t0 = time.time()
+    ch.analyze()
+    analyze_s = time.time() - t0
+    flops = ch.flops()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    st = ch.factor(iterations=args.steps, warmup=args.warmup)   # device-timed per step with CUDA events
+    barrier()
+    # per-step time: the slowest rank (every rank factors the whole problem until the subtree partition lands)
+    step_s = st.seconds_median
+    if world > 1:
+        t = torch.tensor([step_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_s = float(t.item())
+    # end to end through the host-buffer C-ABI call
+    e2e_s = []
+    for _ in range(max(1, args.steps)):
+        _, st2 = ch.factor_host()
+        e2e_s.append(st2.seconds_best)
+    e2e_med = sorted(e2e_s)[len(e2e_s) // 2]
+    if world > 1:
+        t = torch.tensor([e2e_med], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_med = float(t.item())
+    barrier()
+    clocks = sampler.stop(local_rank) if rank == 0 else None
+    kt = ch.kernel_times()      # one instrumented iteration: CUDA events around every launch
+    res = ch.residual(k=2) if ch.n <= 300000 else None
+
+    if rank == 0:
+        peak, peak_how = fp64_peak()
+        gemm_tf = kt["gemm_flops"] / (kt["gemm_ms"] * 1e-3) * 1e-12 if kt["gemm_ms"] > 0 else 0.0
+        tot_ms = kt["potrf_ms"] + kt["trsm_ms"] + kt["gemm_ms"]
+        line = {
+            "metric": METRIC, "value": flops / step_s * 1e-9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": flops / e2e_med * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": ch.nz * 8,
+                    "d2h_bytes_per_step": ch.n * 8, "ms_per_step": e2e_med * 1e3},
+            "gpu_launches": int(st.kernel_launches) * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_grouped (FP64 DMMA)", "achieved": gemm_tf, "peak": peak,
+                         "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_how,
+                         "kernel_share_of_step": kt["gemm_ms"] / tot_ms if tot_ms else None,
+                         "kernel_ms": {k: kt[k] for k in ("potrf_ms", "trsm_ms", "gemm_ms")}},
+            "factor": {"n": ch.n, "nz": ch.nz, "levels": ch.levels, "flops": flops, "factor_GiB": ch.factor_doubles() * 8 / 2**30,
+                       "analyze_s": analyze_s, "assemble_ms": st.assemble_seconds * 1e3, "seconds_best": st.seconds_best,
+                       "residual": res},
+        }
+        if world > 1:
+            line["config"]["parallelism"] = f"{world} ranks, each factors the whole problem (subtree partition not yet landed)"
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_reference(args.workload)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

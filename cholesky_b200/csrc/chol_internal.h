@@ -1,0 +1,133 @@
+// Internal data model of the engine: problem -> symbolic structure -> device schedule.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace chb {
+
+// ----------------------------------------------------------------------------- inputs
+// What the reference reads from its three files (mnd.c:22-199), as plain arrays.
+struct Problem {
+  int n = 0, ncols = 0;
+  int64_t nz = 0;
+  char typecode[4] = {'M', 'C', 'R', 'H'};
+  std::vector<int32_t> ei, ej;  // 0-based, as given (row >= col in the reference's files)
+  std::vector<double> ev;
+  int levels = 0, N = 0;  // N = 2^levels - 1 separators
+  // separators by 1-based heap index h (root = 1, label = N + 1 - h, file id = label - 1)
+  std::vector<int> perm;       // permuted row -> original dof (ascending label == file order)
+  std::vector<int> sz, start;  // [N + 2]
+  std::vector<std::vector<std::vector<int>>> iv;  // iv[h][k]: raw interval list k of separator h
+  int max_int_size = -1;       // as mnd.c:71-150 would return it
+  int level_of(int h) const {
+    int l = 0;
+    while (h > 1) h >>= 1, l++;
+    return l;
+  }
+  int label_of(int h) const { return N + 1 - h; }
+  int heap_of(int label) const { return N + 1 - label; }
+};
+
+int read_problem(Problem &P, const char *mtx, const char *ord, const char *clust, std::string &err);
+int finish_problem(Problem &P, std::string &err);  // start[], validation
+int write_problem(const Problem &P, const char *mtx, const char *ord, const char *clust, std::string &err);
+int generate_problem(Problem &P, int nx, int ny, int nz, int stencil, int levels, std::string &err);
+
+// ----------------------------------------------------------------------------- symbolic
+struct FilledRec {  // reference `Filled` (blas.rg:55-61)
+  int64_t filled, sep_x, sep_y, interval, cluster, lo_x, lo_y, hi_x, hi_y;
+};
+
+// One filled row cluster of block (anc, s) at the time s is eliminated: rows [lo, hi) of
+// separator `anc` (local dof positions), stored at row `off` of s's panel.
+struct Seg {
+  int anc;  // heap index of the row separator (== s for the diagonal block)
+  int lo, hi;
+  int off;
+  int cluster;  // row-cluster index at the elimination interval
+};
+
+struct Symbolic {
+  std::vector<std::vector<std::vector<int>>> cb;  // composed cluster boundaries cb[h][k][j]
+  // supernodal panel of every separator: segs[seg_ptr[h] .. seg_ptr[h+1]); first = diagonal block
+  std::vector<int64_t> seg_ptr;
+  std::vector<Seg> segs;
+  std::vector<int> rows;        // stored rows of the panel (even-aligned segment starts)
+  std::vector<int> ld;          // leading dimension (>= rows, even)
+  std::vector<int64_t> poff;    // panel offset in the factor buffer (doubles)
+  int64_t total_doubles = 0;
+  // pattern evidence
+  std::vector<int64_t> nfilled;
+  std::vector<uint64_t> checksum;
+  std::vector<std::vector<FilledRec>> records;  // only with keep_records
+  int64_t nblocks = 0, nclusters0 = 0;
+  // algorithmic flops / call counts of the reference BLAS call list, per tree level
+  std::vector<double> f_potrf, f_trsm, f_syrk, f_gemm;
+  int64_t calls[4] = {0, 0, 0, 0};
+  double flops() const {
+    double s = 0;
+    for (size_t i = 0; i < f_potrf.size(); i++) s += f_potrf[i] + f_trsm[i] + f_syrk[i] + f_gemm[i];
+    return s;
+  }
+};
+
+int analyze(const Problem &P, Symbolic &S, bool keep_records, std::string &err);
+
+// ----------------------------------------------------------------------------- schedule
+// Everything the device executes is one of three grouped kernels over descriptor arrays.
+// Offsets are in doubles from the factor buffer base, so the schedule is relocatable.
+struct GemmProblem {  // C[M x N] -= sum_c A_c[M x K_c] * B_c[N x K_c]^T  (column-major)
+  int64_t c_off;
+  int ldc, M, N;
+  int tri;  // 1: only i >= j is stored (SYRK on a diagonal cluster / in-panel trailing update)
+  int contrib_begin, contrib_count;
+};
+struct GemmContrib {
+  int64_t a_off, b_off;
+  int lda, ldb, K, pad;
+};
+struct TileRef {  // one CTA
+  int prob;
+  uint16_t tr, tc;
+};
+struct PotrfDesc {  // factor the nb x nb lower tile in place
+  int64_t off;
+  int ld, nb;
+  int col0;  // permuted column of the tile's first column (for info reporting)
+  int pad;
+};
+struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
+  int64_t l_off, b_off;
+  int ld, nb, rows, pad;
+};
+
+enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2 };
+enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
+struct Launch {
+  int kind;
+  int level;
+  int phase;
+  int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
+  double flops;          // executed flops (for per-kernel accounting), GEMM only
+};
+
+struct Schedule {
+  std::vector<GemmProblem> probs;
+  std::vector<GemmContrib> contribs;
+  std::vector<TileRef> tiles;
+  std::vector<PotrfDesc> potrf;
+  std::vector<TrsmDesc> trsm;
+  std::vector<TileRef> trsm_tiles;  // prob = index into trsm[], tr = slab index
+  std::vector<Launch> launches;
+  // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
+  std::vector<int64_t> a_off;
+  int nb = 64, nbo = 256, bm = 64, bn = 64, slab = 64;
+};
+
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string &err);
+
+uint64_t mix64(uint64_t x);
+uint64_t filled_hash(const FilledRec &r);
+
+}  // namespace chb

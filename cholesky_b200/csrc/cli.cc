@@ -1,0 +1,80 @@
+// `cholesky` command line: the reference's flags (mmat.rg:1072-1093) over the C ABI.
+//   -i matrix.mtx -s separators.txt -c clusters.txt [-b rhs.mtx -o solution] [-m factor.mtx]
+//   [-p permuted.mtx] [--iterations N] [--gpu D]
+// Progress lines follow the reference's stdout (mmat.rg:1095-1121, 1228, 1357).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/cholesky.h"
+
+int main(int argc, char **argv) {
+  const char *mat = "", *sep = "", *clu = "", *bfile = "", *sol = "", *fac = "", *perm = "";
+  int iterations = 1, gpu = 0;
+  for (int i = 0; i + 1 < argc; i++) {
+    if (!strcmp(argv[i], "-i")) mat = argv[i + 1];
+    else if (!strcmp(argv[i], "-s")) sep = argv[i + 1];
+    else if (!strcmp(argv[i], "-c")) clu = argv[i + 1];
+    else if (!strcmp(argv[i], "-m")) fac = argv[i + 1];
+    else if (!strcmp(argv[i], "-p")) perm = argv[i + 1];
+    else if (!strcmp(argv[i], "-o")) sol = argv[i + 1];
+    else if (!strcmp(argv[i], "-b")) bfile = argv[i + 1];
+    else if (!strcmp(argv[i], "--iterations")) iterations = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "--gpu")) gpu = atoi(argv[i + 1]);
+  }
+  printf("Iterations: %d\n", iterations);
+  chol_t *c = nullptr;
+  if (chol_create(&gpu, 1, &c)) return 1;
+  if (chol_load(c, mat, sep, clu)) {
+    printf("%s\n", chol_last_error(c));
+    return 1;
+  }
+  printf("M: %d N: %d nz: %lld\n", chol_n(c), chol_n(c), (long long)chol_nz(c));
+  if (chol_analyze(c, 0)) {
+    printf("%s\n", chol_last_error(c));
+    return 1;
+  }
+  printf("levels: %d\nseparators: %d\nMax Interval Size: %d\n", chol_levels(c), chol_num_separators(c), chol_max_int_size(c));
+  printf("Blocks ispace: %lld\nClusters ispace: %lld\n", (long long)chol_num_blocks(c), (long long)chol_num_clusters0(c));
+  if (*perm) {
+    if (chol_assemble(c) || chol_write_factor(c, perm, 0)) {
+      printf("%s\n", chol_last_error(c));
+      return 1;
+    }
+    printf("saving matrix to: %s\n\n", perm);
+  }
+  chol_stats_t st;
+  if (chol_factor(c, iterations, 0, &st)) {
+    printf("%s\n", chol_last_error(c));
+    return 1;
+  }
+  printf("Done factoring: %.6f s (best of %d), %.3f GFLOP/s, %lld kernels per iteration\n", st.seconds_best, iterations,
+         st.flops / st.seconds_best * 1e-9, (long long)st.kernel_launches);
+  if (*fac) {
+    printf("saving matrix to: %s\n\n", fac);
+    if (chol_write_factor(c, fac, 0)) {
+      printf("%s\n", chol_last_error(c));
+      return 1;
+    }
+  }
+  if (*bfile) {
+    int n = chol_n(c);
+    std::vector<double> b(n), x(n);
+    if (chol_read_vector(bfile, n, b.data())) {
+      printf("cannot read %s\n", bfile);
+      return 1;
+    }
+    if (chol_solve(c, b.data(), x.data())) {
+      printf("%s\n", chol_last_error(c));
+      return 1;
+    }
+    printf("Done solve.\n");
+    if (*sol) {
+      printf("Saving solution to: %s\n", sol);
+      chol_write_solution(sol, n, x.data());
+    }
+  }
+  chol_destroy(c);
+  return 0;
+}

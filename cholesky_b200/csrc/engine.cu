@@ -1,0 +1,615 @@
+// C ABI of the engine (include/cholesky.h): handle, loaders, host symbolic analysis, GPU numeric
+// factorization driven by the compiled level schedule, result access.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/chol_mmio.h"
+#include "../../include/chol_mnd.h"
+#include "../../include/cholesky.h"
+#include "chol_internal.h"
+#include "kernels.cuh"
+
+using namespace chb;
+
+typedef GemmCfg<64, 64, 16, 32, 32, 3> Gemm64;
+
+struct chol {
+  std::string err;
+  int device = 0;
+  Problem P;
+  Symbolic S;
+  Schedule D;
+  bool loaded = false, analyzed = false, device_ready = false, assembled = false;
+  cudaStream_t stream = nullptr;
+  double *d_fac = nullptr;
+  double *d_vals = nullptr;
+  int64_t *d_aoff = nullptr;
+  GemmProblem *d_probs = nullptr;
+  GemmContrib *d_contribs = nullptr;
+  TileRef *d_tiles = nullptr;
+  PotrfDesc *d_potrf = nullptr;
+  TrsmDesc *d_trsm = nullptr;
+  TileRef *d_trsm_tiles = nullptr;
+  int *d_info = nullptr;
+  int64_t *d_diag_off = nullptr;
+  double *d_diag = nullptr;
+  double *h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+  std::vector<double> h_fac;  // host copy of the factor, fetched lazily
+  bool h_fac_valid = false;
+  double k_ms[3] = {0, 0, 0};
+  double k_gemm_flops = 0;
+};
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+      return -100;                                                                                \
+    }                                                                                             \
+  } while (0)
+
+static int fail(chol_t *c, const std::string &m) {
+  c->err = m;
+  return -1;
+}
+
+extern "C" {
+
+void register_mappers(void) {}
+
+int chol_create(const int *devices, int ngpu, chol_t **out) {
+  if (!out) return -1;
+  chol_t *c = new chol();
+  c->device = (devices && ngpu > 0) ? devices[0] : 0;
+  *out = c;
+  return 0;
+}
+
+static void free_device(chol_t *c) {
+  if (!c->device_ready) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
+  cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_info);
+  cudaFree(c->d_diag_off), cudaFree(c->d_diag);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  c->device_ready = false;
+}
+
+void chol_destroy(chol_t *c) {
+  if (!c) return;
+  free_device(c);
+  delete c;
+}
+const char *chol_last_error(chol_t *c) { return c ? c->err.c_str() : "null handle"; }
+
+int chol_load(chol_t *c, const char *mtx, const char *ord, const char *clust) {
+  c->loaded = c->analyzed = false;
+  if (read_problem(c->P, mtx, ord, clust, c->err)) return -1;
+  c->loaded = true;
+  return 0;
+}
+
+int chol_load_arrays(chol_t *c, int n, int64_t nz, const int32_t *I, const int32_t *J, const double *V, int levels, int nsep,
+                     const int64_t *sep_ptr, const int32_t *sep_dofs, const int64_t *sep_iv_ptr, const int64_t *iv_ptr,
+                     const int32_t *iv_vals) {
+  c->loaded = c->analyzed = false;
+  Problem &P = c->P;
+  P = Problem();
+  P.n = P.ncols = n, P.nz = nz;
+  P.ei.assign(I, I + nz), P.ej.assign(J, J + nz), P.ev.assign(V, V + nz);
+  P.levels = levels, P.N = nsep;
+  if (nsep != (1 << levels) - 1) return fail(c, "num_separators != 2^levels - 1");
+  P.perm.assign(sep_dofs, sep_dofs + sep_ptr[nsep]);
+  if ((int)P.perm.size() != n) return fail(c, "separator lists do not cover the matrix");
+  P.sz.assign(nsep + 2, 0);
+  P.iv.assign(nsep + 2, {});
+  int mx = -1;
+  for (int id = 0; id < nsep; id++) {
+    int h = P.heap_of(id + 1);
+    P.sz[h] = (int)(sep_ptr[id + 1] - sep_ptr[id]);
+    for (int64_t k = sep_iv_ptr[id]; k < sep_iv_ptr[id + 1]; k++) {
+      P.iv[h].emplace_back(iv_vals + iv_ptr[k], iv_vals + iv_ptr[k + 1]);
+      mx = std::max(mx, (int)(iv_ptr[k + 1] - iv_ptr[k]) + 1);
+    }
+  }
+  P.max_int_size = mx;
+  if (finish_problem(P, c->err)) return -1;
+  c->loaded = true;
+  return 0;
+}
+
+int chol_generate(chol_t *c, int nx, int ny, int nz, int stencil, int levels) {
+  c->loaded = c->analyzed = false;
+  if (generate_problem(c->P, nx, ny, nz, stencil, levels, c->err)) return -1;
+  c->loaded = true;
+  return 0;
+}
+
+int chol_write_inputs(chol_t *c, const char *mtx, const char *ord, const char *clust) {
+  if (!c->loaded) return fail(c, "nothing loaded");
+  return write_problem(c->P, mtx, ord, clust, c->err);
+}
+
+int chol_analyze(chol_t *c, int keep_records) {
+  if (!c->loaded) return fail(c, "load a problem first");
+  free_device(c);
+  c->analyzed = false;
+  if (analyze(c->P, c->S, keep_records != 0, c->err)) return -1;
+  if (build_schedule(c->P, c->S, c->D, c->err)) return -1;
+  c->analyzed = true;
+  c->assembled = false;
+  c->h_fac_valid = false;
+  return 0;
+}
+
+int chol_n(chol_t *c) { return c->P.n; }
+int64_t chol_nz(chol_t *c) { return c->P.nz; }
+int chol_levels(chol_t *c) { return c->P.levels; }
+int chol_num_separators(chol_t *c) { return c->P.N; }
+int chol_max_int_size(chol_t *c) { return c->P.max_int_size; }
+int64_t chol_num_blocks(chol_t *c) { return c->S.nblocks; }
+int64_t chol_num_clusters0(chol_t *c) { return c->S.nclusters0; }
+int chol_get_perm(chol_t *c, int32_t *perm) {
+  for (int p = 0; p < c->P.n; p++) perm[p] = c->P.perm[p];
+  return 0;
+}
+int chol_get_sep_sizes(chol_t *c, int32_t *sizes) {
+  for (int label = 1; label <= c->P.N; label++) sizes[label - 1] = c->P.sz[c->P.heap_of(label)];
+  return 0;
+}
+/* partition_matrix, mmat.rg:299-362 */
+int64_t chol_get_block_bounds(chol_t *c, int64_t *out) {
+  const Problem &P = c->P;
+  int64_t k = 0;
+  for (int hc = 1; hc <= P.N; hc++)
+    for (int hr = hc; hr >= 1; hr >>= 1) {
+      if (out) {
+        int64_t *r = out + 6 * k;
+        r[0] = P.label_of(hr), r[1] = P.label_of(hc);
+        r[2] = P.start[hr], r[3] = P.start[hc];
+        r[4] = P.start[hr] + P.sz[hr] - 1, r[5] = P.start[hc] + P.sz[hc] - 1;
+      }
+      k++;
+    }
+  return k;
+}
+int64_t chol_num_filled(chol_t *c, int t) { return (!c->analyzed || t < 0 || t >= c->P.levels) ? -1 : c->S.nfilled[t]; }
+int64_t chol_get_filled(chol_t *c, int t, chol_filled_t *out) {
+  if (!c->analyzed || t < 0 || t >= c->P.levels) return -1;
+  if (c->S.records.empty()) return fail(c, "analyze with keep_records to read Filled records");
+  const auto &r = c->S.records[t];
+  static_assert(sizeof(chol_filled_t) == sizeof(FilledRec), "layout");
+  memcpy(out, r.data(), r.size() * sizeof(FilledRec));
+  return (int64_t)r.size();
+}
+uint64_t chol_filled_checksum(chol_t *c, int t) { return (!c->analyzed || t < 0 || t >= c->P.levels) ? 0 : c->S.checksum[t]; }
+double chol_flops(chol_t *c) { return c->S.flops(); }
+int chol_flops_by_level(chol_t *c, double *p, double *t, double *s, double *g) {
+  for (int l = 0; l < c->P.levels; l++) p[l] = c->S.f_potrf[l], t[l] = c->S.f_trsm[l], s[l] = c->S.f_syrk[l], g[l] = c->S.f_gemm[l];
+  return 0;
+}
+int chol_call_counts(chol_t *c, int64_t *c4) {
+  for (int i = 0; i < 4; i++) c4[i] = c->S.calls[i];
+  return 0;
+}
+int64_t chol_factor_doubles(chol_t *c) { return c->S.total_doubles; }
+
+// ------------------------------------------------------------------------------ device side
+}  // extern "C"
+template <typename T>
+static int upload(chol_t *c, T **dst, const std::vector<T> &src) {
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  CK(cudaMalloc((void **)dst, bytes));
+  if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" {
+static int ensure_device(chol_t *c) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  if (c->device_ready) return 0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(c, "no CUDA device: the numeric factorization runs on the GPU only (no CPU fallback)");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc((void **)&c->d_fac, (size_t)c->S.total_doubles * sizeof(double)));
+  c->device_ready = true;
+  if (upload(c, &c->d_vals, c->P.ev)) return -100;
+  if (upload(c, &c->d_aoff, c->D.a_off)) return -100;
+  if (upload(c, &c->d_probs, c->D.probs)) return -100;
+  if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
+  if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
+  if (upload(c, &c->d_potrf, c->D.potrf)) return -100;
+  if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
+  if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
+  CK(cudaMalloc((void **)&c->d_info, sizeof(int)));
+  std::vector<int64_t> doff(c->P.n);
+  for (int h = 1; h <= c->P.N; h++)
+    for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
+  if (upload(c, &c->d_diag_off, doff)) return -100;
+  CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
+  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
+  return 0;
+}
+
+static int do_assemble(chol_t *c) {
+  CK(cudaMemsetAsync(c->d_fac, 0, (size_t)c->S.total_doubles * sizeof(double), c->stream));
+  int info0 = 0x7fffffff;
+  CK(cudaMemcpyAsync(c->d_info, &info0, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (c->P.nz > 0) {
+    int64_t nzv = c->P.nz;
+    assemble_kernel<<<(unsigned)((nzv + 255) / 256), 256, 0, c->stream>>>(c->d_vals, c->d_aoff, nzv, c->d_fac);
+  }
+  CK(cudaGetLastError());
+  c->assembled = true;
+  c->h_fac_valid = false;
+  return 0;
+}
+
+static int run_launch(chol_t *c, const Launch &l) {
+  switch (l.kind) {
+    case K_POTRF:
+      potrf_tile<<<(unsigned)l.count, 256, 0, c->stream>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      break;
+    case K_TRSM:
+      trsm_tile<<<(unsigned)l.count, 64, 0, c->stream>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      break;
+    case K_GEMM:
+      gemm_grouped<64, 64, 16, 32, 32, 3><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
+          c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
+      break;
+  }
+  return 0;
+}
+
+static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool per_kernel_timing) {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kinds;
+  std::vector<double> fl;
+  for (const Launch &l : c->D.launches) {
+    if (l.level > lvl_from || l.level < lvl_to || !(l.phase & phase_mask)) continue;
+    if (per_kernel_timing) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a), cudaEventCreate(&b);
+      cudaEventRecord(a, c->stream);
+      run_launch(c, l);
+      cudaEventRecord(b, c->stream);
+      ev.push_back(a), ev.push_back(b), kinds.push_back(l.kind), fl.push_back(l.flops);
+    } else
+      run_launch(c, l);
+  }
+  CK(cudaGetLastError());
+  if (per_kernel_timing) {
+    CK(cudaStreamSynchronize(c->stream));
+    c->k_ms[0] = c->k_ms[1] = c->k_ms[2] = 0, c->k_gemm_flops = 0;
+    for (size_t i = 0; i < kinds.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+      c->k_ms[kinds[i]] += ms;
+      if (kinds[i] == K_GEMM) c->k_gemm_flops += fl[i];
+      cudaEventDestroy(ev[2 * i]), cudaEventDestroy(ev[2 * i + 1]);
+    }
+  }
+  return 0;
+}
+
+int chol_assemble(chol_t *c) {
+  if (ensure_device(c)) return -1;
+  if (do_assemble(c)) return -1;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int fetch_info(chol_t *c, int *info) {
+  int v = 0;
+  CK(cudaMemcpyAsync(&v, c->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *info = (v == 0x7fffffff) ? 0 : v;
+  return 0;
+}
+
+int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
+  if (ensure_device(c)) return -1;
+  if (iterations < 1) iterations = 1;
+  std::vector<double> secs;
+  double asm_s = 0;
+  cudaEvent_t e0, e1, e2;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventCreate(&e2));
+  for (int it = 0; it < warmup + iterations; it++) {
+    CK(cudaEventRecord(e0, c->stream));
+    if (do_assemble(c)) return -1;
+    CK(cudaEventRecord(e1, c->stream));
+    if (run_levels(c, c->P.levels - 1, 0, 7, false)) return -1;
+    CK(cudaEventRecord(e2, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ma = 0, mf = 0;
+    CK(cudaEventElapsedTime(&ma, e0, e1));
+    CK(cudaEventElapsedTime(&mf, e1, e2));
+    if (it >= warmup) secs.push_back(mf * 1e-3), asm_s = ma * 1e-3;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2);
+  int info = 0;
+  if (fetch_info(c, &info)) return -1;
+  if (st) {
+    std::vector<double> s = secs;
+    std::sort(s.begin(), s.end());
+    st->seconds_best = s.front();
+    st->seconds_median = s[s.size() / 2];
+    st->seconds_last = secs.back();
+    st->assemble_seconds = asm_s;
+    st->flops = c->S.flops();
+    st->kernel_launches = (int64_t)c->D.launches.size();
+    st->info = info;
+  }
+  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  return 0;
+}
+
+static int piecewise(chol_t *c, int lvl, int phase) {
+  if (ensure_device(c)) return -1;
+  if (!c->assembled) return fail(c, "assemble first");
+  if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
+  c->h_fac_valid = false;
+  if (run_levels(c, lvl, lvl, phase, false)) return -1;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int chol_fused_dpotrf(chol_t *c, int lvl) { return piecewise(c, lvl, PH_POTRF); }
+int chol_fused_dtrsm(chol_t *c, int lvl) { return piecewise(c, lvl, PH_TRSM); }
+int chol_fused_update(chol_t *c, int lvl) { return piecewise(c, lvl, PH_UPDATE); }
+
+int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_out, chol_stats_t *st) {
+  if (ensure_device(c)) return -1;
+  if (values && nz != c->P.nz) return fail(c, "value count differs from the loaded pattern");
+  size_t need = std::max((size_t)c->P.nz, (size_t)c->P.n) * sizeof(double);
+  if (c->h_pinned_bytes < need) {
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    CK(cudaMallocHost((void **)&c->h_pinned, need));
+    c->h_pinned_bytes = need;
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, c->stream));
+  const double *src = values ? values : c->P.ev.data();
+  memcpy(c->h_pinned, src, (size_t)c->P.nz * sizeof(double));
+  CK(cudaMemcpyAsync(c->d_vals, c->h_pinned, (size_t)c->P.nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (do_assemble(c)) return -1;
+  if (run_levels(c, c->P.levels - 1, 0, 7, false)) return -1;
+  gather_diag_kernel<<<(c->P.n + 255) / 256, 256, 0, c->stream>>>(c->d_diag_off, c->P.n, c->d_fac, c->d_diag);
+  CK(cudaMemcpyAsync(c->h_pinned, c->d_diag, (size_t)c->P.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(e1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  if (diag_out) memcpy(diag_out, c->h_pinned, (size_t)c->P.n * sizeof(double));
+  int info = 0;
+  if (fetch_info(c, &info)) return -1;
+  if (st) {
+    st->seconds_best = st->seconds_median = st->seconds_last = ms * 1e-3;
+    st->assemble_seconds = 0;
+    st->flops = c->S.flops();
+    st->kernel_launches = (int64_t)c->D.launches.size() + 2;
+    st->info = info;
+  }
+  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  return 0;
+}
+
+int chol_synchronize(chol_t *c) {
+  if (!c->device_ready) return 0;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops) {
+  if (ensure_device(c)) return -1;
+  if (do_assemble(c)) return -1;
+  if (run_levels(c, c->P.levels - 1, 0, 7, true)) return -1;
+  if (potrf_ms) *potrf_ms = c->k_ms[K_POTRF];
+  if (trsm_ms) *trsm_ms = c->k_ms[K_TRSM];
+  if (gemm_ms) *gemm_ms = c->k_ms[K_GEMM];
+  if (gemm_flops) *gemm_flops = c->k_gemm_flops;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ results
+static int fetch_factor(chol_t *c) {
+  if (!c->device_ready || !c->assembled) return fail(c, "nothing factored yet");
+  if (c->h_fac_valid) return 0;
+  c->h_fac.resize((size_t)c->S.total_doubles);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(c->h_fac.data(), c->d_fac, (size_t)c->S.total_doubles * sizeof(double), cudaMemcpyDeviceToHost));
+  c->h_fac_valid = true;
+  return 0;
+}
+
+// visit stored entries != 0 block by block ((row_sep, col_sep) ascending labels), row-major inside
+// a block, as write_matrix does (mmat.rg:114-144)
+}  // extern "C"
+template <typename F>
+static void visit(chol_t *c, F fn) {
+  const Problem &P = c->P;
+  const Symbolic &S = c->S;
+  // blocks of row separator r: column separators r and its descendants
+  for (int lr = 1; lr <= P.N; lr++) {
+    int hr = P.heap_of(lr), lv = P.level_of(hr);
+    std::vector<int> cols;
+    for (int d = 0; lv + d < P.levels; d++)
+      for (int hc = hr << d; hc < ((hr + 1) << d); hc++) cols.push_back(hc);
+    std::sort(cols.begin(), cols.end(), [](int a, int b) { return a > b; });  // ascending label
+    for (int hc : cols) {
+      const double *pan = c->h_fac.data() + S.poff[hc];
+      int ld = S.ld[hc];
+      for (int64_t s = S.seg_ptr[hc]; s < S.seg_ptr[hc + 1]; s++) {
+        const Seg &sg = S.segs[s];
+        if (sg.anc != hr) continue;
+        for (int r = 0; r < sg.hi - sg.lo; r++)
+          for (int col = 0; col < P.sz[hc]; col++) {
+            double v = pan[sg.off + r + (size_t)col * ld];
+            if (v != 0) fn(P.start[hr] + sg.lo + r, P.start[hc] + col, v);
+          }
+      }
+    }
+  }
+}
+
+extern "C" {
+int64_t chol_factor_nnz(chol_t *c) {
+  if (fetch_factor(c)) return -1;
+  int64_t k = 0;
+  visit(c, [&](int, int, double) { k++; });
+  return k;
+}
+int64_t chol_get_factor_coo(chol_t *c, int32_t *I, int32_t *J, double *V) {
+  if (fetch_factor(c)) return -1;
+  int64_t k = 0;
+  visit(c, [&](int i, int j, double v) { I[k] = i, J[k] = j, V[k] = v, k++; });
+  return k;
+}
+int chol_get_factor_dense(chol_t *c, double *out) {
+  if (fetch_factor(c)) return -1;
+  size_t n = (size_t)c->P.n;
+  memset(out, 0, n * n * sizeof(double));
+  visit(c, [&](int i, int j, double v) { out[(size_t)i * n + j] = v; });
+  return 0;
+}
+int chol_write_factor(chol_t *c, const char *path, int full) {
+  if (fetch_factor(c)) return -1;
+  FILE *f = fopen(path, "w");
+  if (!f) return fail(c, std::string("cannot write ") + path);
+  int64_t nnz = 0;
+  visit(c, [&](int, int, double) { nnz++; });
+  MM_typecode tc;
+  memcpy(tc, c->P.typecode, 4);
+  mm_write_banner(f, tc);
+  mm_write_mtx_crd_size(f, c->P.n, c->P.ncols, (int)nnz);
+  visit(c, [&](int i, int j, double v) { fprintf(f, full ? "%d %d %.17g\n" : "%d %d %0.8g\n", i + 1, j + 1, v); });
+  fclose(f);
+  return 0;
+}
+
+int chol_residual(chol_t *c, int k, uint64_t seed, double *rel) {
+  // host evaluation over the stored pattern: R = A W - L (L^T W)
+  if (fetch_factor(c)) return -1;
+  const Problem &P = c->P;
+  const Symbolic &S = c->S;
+  size_t n = (size_t)P.n;
+  if (k < 1) k = 1;
+  std::vector<double> W(n * k), Y(n * k, 0.0), Z(n * k, 0.0), AW(n * k, 0.0);
+  uint64_t s = seed ? seed : 1;
+  for (auto &w : W) {
+    s = mix64(s);
+    w = (s & 1) ? 1.0 : -1.0;
+  }
+  // W is indexed by permuted row
+  std::vector<int> iperm(n);
+  for (int p = 0; p < P.n; p++) iperm[P.perm[p]] = p;
+  for (int64_t e = 0; e < P.nz; e++) {
+    int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
+    double v = P.ev[e];
+    for (int q = 0; q < k; q++) {
+      AW[(size_t)pi * k + q] += v * W[(size_t)pj * k + q];
+      if (pi != pj) AW[(size_t)pj * k + q] += v * W[(size_t)pi * k + q];
+    }
+  }
+  // Y = L^T W (by columns of L), Z = L Y
+  for (int pass = 0; pass < 2; pass++)
+    for (int hc = 1; hc <= P.N; hc++) {
+      const double *pan = c->h_fac.data() + S.poff[hc];
+      int ld = S.ld[hc];
+      for (int64_t sgi = S.seg_ptr[hc]; sgi < S.seg_ptr[hc + 1]; sgi++) {
+        const Seg &sg = S.segs[sgi];
+        bool diag = sg.anc == hc;
+        for (int col = 0; col < P.sz[hc]; col++) {
+          size_t gc = (size_t)P.start[hc] + col;
+          for (int r = diag ? col : 0; r < sg.hi - sg.lo; r++) {
+            double v = pan[sg.off + r + (size_t)col * ld];
+            if (v == 0) continue;
+            size_t gr = (size_t)P.start[sg.anc] + sg.lo + r;
+            for (int q = 0; q < k; q++) {
+              if (pass == 0) Y[gc * k + q] += v * W[gr * k + q];
+              else Z[gr * k + q] += v * Y[gc * k + q];
+            }
+          }
+        }
+      }
+    }
+  double num = 0, den = 0;
+  for (size_t i = 0; i < n * k; i++) num += (AW[i] - Z[i]) * (AW[i] - Z[i]), den += AW[i] * AW[i];
+  *rel = std::sqrt(num / (den > 0 ? den : 1));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ solve (host substitution over the GPU factor)
+int chol_solve(chol_t *c, const double *b, double *x) {
+  if (fetch_factor(c)) return -1;
+  const Problem &P = c->P;
+  const Symbolic &S = c->S;
+  std::vector<double> v((size_t)P.n);
+  for (int p = 0; p < P.n; p++) v[p] = b[P.perm[p]];
+  // forward: leaves to root (mmat.rg:1394-1435)
+  for (int lvl = P.levels - 1; lvl >= 0; lvl--)
+    for (int hs = 1 << lvl; hs < (1 << (lvl + 1)); hs++) {
+      const double *pan = c->h_fac.data() + S.poff[hs];
+      int ld = S.ld[hs], n = P.sz[hs];
+      double *vs = v.data() + P.start[hs];
+      for (int j = 0; j < n; j++) {
+        vs[j] /= pan[j + (size_t)j * ld];
+        for (int i = j + 1; i < n; i++) vs[i] -= pan[i + (size_t)j * ld] * vs[j];
+      }
+      for (int64_t sgi = S.seg_ptr[hs] + 1; sgi < S.seg_ptr[hs + 1]; sgi++) {
+        const Seg &sg = S.segs[sgi];
+        double *vp = v.data() + P.start[sg.anc] + sg.lo;
+        for (int j = 0; j < n; j++)
+          for (int r = 0; r < sg.hi - sg.lo; r++) vp[r] -= pan[sg.off + r + (size_t)j * ld] * vs[j];
+      }
+    }
+  // backward: root to leaves (mmat.rg:1437-1479)
+  for (int lvl = 0; lvl < P.levels; lvl++)
+    for (int hs = 1 << lvl; hs < (1 << (lvl + 1)); hs++) {
+      const double *pan = c->h_fac.data() + S.poff[hs];
+      int ld = S.ld[hs], n = P.sz[hs];
+      double *vs = v.data() + P.start[hs];
+      for (int64_t sgi = S.seg_ptr[hs] + 1; sgi < S.seg_ptr[hs + 1]; sgi++) {
+        const Seg &sg = S.segs[sgi];
+        const double *vp = v.data() + P.start[sg.anc] + sg.lo;
+        for (int j = 0; j < n; j++) {
+          double acc = 0;
+          for (int r = 0; r < sg.hi - sg.lo; r++) acc += pan[sg.off + r + (size_t)j * ld] * vp[r];
+          vs[j] -= acc;
+        }
+      }
+      for (int j = n - 1; j >= 0; j--) {
+        double acc = vs[j];
+        for (int i = j + 1; i < n; i++) acc -= pan[i + (size_t)j * ld] * vs[i];
+        vs[j] = acc / pan[j + (size_t)j * ld];
+      }
+    }
+  for (int p = 0; p < P.n; p++) x[P.perm[p]] = v[p];
+  return 0;
+}
+
+int chol_read_vector(const char *path, int n, double *out) { return mnd_read_vector(path, n, out); }
+int chol_write_solution(const char *path, int n, const double *x) { /* mmat.rg:785-798 */
+  FILE *f = fopen(path, "w");
+  if (!f) return -1;
+  for (int i = 0; i < n; i++) fprintf(f, "%0.8g\n", x[i]);
+  fclose(f);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// sm_100a kernels of the numeric factorization.  Three grouped kernels execute the whole level
+// schedule (see schedule.cc); one scatter kernel assembles A.
+//
+//   gemm_grouped   C -= sum_c A_c B_c^T on FP64 tensor cores (mma.sync DMMA m8n8k4), operands
+//                  staged through shared memory by a multi-stage cp.async pipeline, one CTA per
+//                  destination tile, contributors accumulated in registers in a fixed order
+//                  (atomic-free, deterministic), lower-triangle masking for SYRK destinations.
+//                  Replaces cblas_dgemm / cblas_dsyrk as called at blas.rg:139-142, 187-189.
+//   potrf_tile     in-shared-memory Cholesky of one NB x NB pivot tile (LAPACKE_dpotrf, blas.rg:71).
+//   trsm_tile      one 64-row slab times L^-T by forward substitution, one row per thread
+//                  (cblas_dtrsm Right/Lower/Trans/NonUnit, blas.rg:99-100).
+//   assemble       factor[a_off[e]] = value[e]   (fill_block, mmat.rg:529-633).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chol_internal.h"
+
+namespace chb {
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); lane = 4*g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+struct GemmCfg {
+  static constexpr int kWarpsM = BM / WM, kWarpsN = BN / WN;
+  static constexpr int kThreads = kWarpsM * kWarpsN * 32;
+  static constexpr int kPad = 4;  // row stride = 4 mod 16 doubles: conflict-free DMMA fragment loads
+  static constexpr int kLdA = BM + kPad, kLdB = BN + kPad;
+  static constexpr int kStageDoubles = BK * (kLdA + kLdB);
+  static constexpr int kSmemBytes = STAGES * kStageDoubles * 8;
+};
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
+    gemm_grouped(const GemmProblem *__restrict__ probs, const GemmContrib *__restrict__ contribs,
+                 const TileRef *__restrict__ tiles, double *__restrict__ fac) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES>;
+  extern __shared__ __align__(16) double smem[];
+  const TileRef tile = tiles[blockIdx.x];
+  const GemmProblem pr = probs[tile.prob];
+  const int row0 = tile.tr * BM, col0 = tile.tc * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % Cfg::kWarpsM) * WM, wn0 = (warp / Cfg::kWarpsM) * WN;
+  constexpr int MB = WM / 8, NBk = WN / 8;
+  double acc[MB][NBk][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NBk; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int mrem = pr.M - row0, nrem = pr.N - col0;  // valid rows of A / B in this tile (may exceed BM/BN)
+
+  for (int c = 0; c < pr.contrib_count; c++) {
+    const GemmContrib cb = contribs[pr.contrib_begin + c];
+    const double *__restrict__ A = fac + cb.a_off + row0;
+    const double *__restrict__ Bp = fac + cb.b_off + col0;
+    const int K = cb.K, lda = cb.lda, ldb = cb.ldb;
+    const int nk = (K + BK - 1) / BK;
+
+    auto load_stage = [&](int stage, int kt) {
+      double *As = smem + stage * Cfg::kStageDoubles;
+      double *Bs = As + BK * Cfg::kLdA;
+      const int k0 = kt * BK;
+#pragma unroll
+      for (int i = tid; i < BK * (BM / 2); i += Cfg::kThreads) {
+        int kk = i / (BM / 2), m2 = (i % (BM / 2)) * 2;
+        bool ok = (m2 < mrem) && (k0 + kk < K);
+        cp_async16(As + kk * Cfg::kLdA + m2, ok ? (A + m2 + (size_t)(k0 + kk) * lda) : A, ok);
+      }
+#pragma unroll
+      for (int i = tid; i < BK * (BN / 2); i += Cfg::kThreads) {
+        int kk = i / (BN / 2), n2 = (i % (BN / 2)) * 2;
+        bool ok = (n2 < nrem) && (k0 + kk < K);
+        cp_async16(Bs + kk * Cfg::kLdB + n2, ok ? (Bp + n2 + (size_t)(k0 + kk) * ldb) : Bp, ok);
+      }
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+      if (s < nk) load_stage(s, s);
+      cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      int nxt = kt + STAGES - 1;
+      if (nxt < nk) load_stage(nxt % STAGES, nxt);
+      cp_async_commit();
+      const double *As = smem + (kt % STAGES) * Cfg::kStageDoubles;
+      const double *Bs = As + BK * Cfg::kLdA;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; k4++) {
+        double a[MB], b[NBk];
+#pragma unroll
+        for (int i = 0; i < MB; i++) a[i] = As[(k4 * 4 + t) * Cfg::kLdA + wm0 + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < NBk; j++) b[j] = Bs[(k4 * 4 + t) * Cfg::kLdB + wn0 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < MB; i++)
+#pragma unroll
+          for (int j = 0; j < NBk; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+
+  double *__restrict__ C = fac + pr.c_off;
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int r = row0 + wm0 + i * 8 + g;
+    if (r >= pr.M) continue;
+#pragma unroll
+    for (int j = 0; j < NBk; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+        if (cc < pr.N && (!pr.tri || r >= cc)) {
+          double *p = C + r + (size_t)cc * pr.ldc;
+          *p -= acc[i][j][e];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kNB = 64;
+
+__global__ void __launch_bounds__(256) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac, int *__restrict__ info) {
+  __shared__ double T[kNB][kNB + 1];
+  const PotrfDesc d = descs[blockIdx.x];
+  double *__restrict__ A = fac + d.off;
+  const int nb = d.nb, tid = threadIdx.x;
+  for (int i = tid; i < nb * nb; i += 256) {
+    int r = i % nb, c = i / nb;
+    T[r][c] = (r >= c) ? A[r + (size_t)c * d.ld] : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; k++) {
+    if (tid == 0) {
+      double v = T[k][k];
+      if (!(v > 0.0)) {
+        atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+        v = 1.0;
+      }
+      T[k][k] = sqrt(v);
+    }
+    __syncthreads();
+    const double dk = T[k][k];
+    for (int i = k + 1 + tid; i < nb; i += 256) T[i][k] /= dk;
+    __syncthreads();
+    const int rem = nb - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += 256) {
+      int i = k + 1 + idx % rem, j = k + 1 + idx / rem;
+      if (i >= j) T[i][j] -= T[i][k] * T[j][k];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < nb * nb; i += 256) {
+    int r = i % nb, c = i / nb;
+    if (r >= c) A[r + (size_t)c * d.ld] = T[r][c];
+  }
+}
+
+__global__ void __launch_bounds__(64) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
+                                                double *__restrict__ fac) {
+  __shared__ double Ls[kNB][kNB + 1];  // Ls[c][k] = L[c][k]
+  const TileRef tl = tiles[blockIdx.x];
+  const TrsmDesc d = descs[tl.prob];
+  const int slab = (int)tl.tr | ((int)tl.tc << 16);
+  const int tid = threadIdx.x, nb = d.nb;
+  const double *__restrict__ Lg = fac + d.l_off;
+  for (int i = tid; i < kNB * kNB; i += 64) {
+    int r = i % kNB, c = i / kNB;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < nb && c < nb && r >= c) v = Lg[r + (size_t)c * d.ld];
+    Ls[r][c] = v;
+  }
+  __syncthreads();
+  const int row = slab * 64 + tid;
+  if (row >= d.rows) return;
+  double *__restrict__ Bp = fac + d.b_off + row;
+  double x[kNB];
+#pragma unroll
+  for (int c = 0; c < kNB; c++) x[c] = (c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+#pragma unroll
+  for (int c = 0; c < kNB; c++) {
+    double s = x[c];
+#pragma unroll
+    for (int k = 0; k < c; k++) s -= x[k] * Ls[c][k];
+    x[c] = s / Ls[c][c];
+  }
+#pragma unroll
+  for (int c = 0; c < kNB; c++)
+    if (c < nb) Bp[(size_t)c * d.ld] = x[c];
+}
+
+__global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *__restrict__ offs, int64_t nz, double *__restrict__ fac) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nz) {
+    int64_t o = offs[e];
+    if (o >= 0) fac[o] = vals[e];
+  }
+}
+
+__global__ void gather_diag_kernel(const int64_t *__restrict__ diag_off, int n, const double *__restrict__ fac, double *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fac[diag_off[i]];
+}
+
+}  // namespace chb

@@ -1,0 +1,200 @@
+"""Host-side mirror of the reference's program for the factorization path (mmat.rg main, 1056-1362):
+load (-i/-s/-c), symbolic analysis, numeric factorization on the GPU, factor output (-m).  Everything
+numeric happens inside libcholesky_b200.so (CUDA, sm_100a)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class CholeskyError(RuntimeError):
+    pass
+
+
+class Cholesky:
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        self.h = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        if self.L.chol_create(dev, 1, C.byref(self.h)) != 0:
+            raise CholeskyError("chol_create failed")
+
+    # ---- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.chol_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CholeskyError(self.L.chol_last_error(self.h).decode())
+
+    # ---- inputs (mmat.rg:1097-1130)
+    def load(self, matrix, separators, clusters):
+        self._ck(self.L.chol_load(self.h, matrix.encode(), separators.encode(), clusters.encode()))
+        return self
+
+    def generate(self, nx, ny=1, nz=1, stencil=7, levels=0):
+        self._ck(self.L.chol_generate(self.h, nx, ny, nz, stencil, levels))
+        return self
+
+    def write_inputs(self, matrix=None, separators=None, clusters=None):
+        def enc(s):
+            return s.encode() if s else None
+        self._ck(self.L.chol_write_inputs(self.h, enc(matrix), enc(separators), enc(clusters)))
+
+    # ---- symbolic (mmat.rg:1134-1209)
+    def analyze(self, keep_records=False):
+        self._ck(self.L.chol_analyze(self.h, 1 if keep_records else 0))
+        self.n = self.L.chol_n(self.h)
+        self.nz = int(self.L.chol_nz(self.h))
+        self.levels = self.L.chol_levels(self.h)
+        self.num_separators = self.L.chol_num_separators(self.h)
+        return self
+
+    def perm(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        self.L.chol_get_perm(self.h, _p(out))
+        return out
+
+    def sep_sizes(self):
+        out = np.zeros(self.num_separators, dtype=np.int32)
+        self.L.chol_get_sep_sizes(self.h, _p(out))
+        return out
+
+    def block_bounds(self):
+        k = self.L.chol_get_block_bounds(self.h, None)
+        out = np.zeros((k, 6), dtype=np.int64)
+        self.L.chol_get_block_bounds(self.h, _p(out))
+        return out
+
+    def num_blocks(self):
+        return int(self.L.chol_num_blocks(self.h))
+
+    def num_clusters0(self):
+        return int(self.L.chol_num_clusters0(self.h))
+
+    def max_int_size(self):
+        return int(self.L.chol_max_int_size(self.h))
+
+    def num_filled(self, lbl):
+        return int(self.L.chol_num_filled(self.h, lbl))
+
+    def filled(self, lbl):
+        k = self.num_filled(lbl)
+        out = np.zeros((max(k, 1), 9), dtype=np.int64)
+        got = self.L.chol_get_filled(self.h, lbl, _p(out))
+        if got < 0:
+            raise CholeskyError(self.L.chol_last_error(self.h).decode())
+        return out[:k]
+
+    def filled_checksum(self, lbl):
+        return int(self.L.chol_filled_checksum(self.h, lbl))
+
+    def flops(self):
+        return float(self.L.chol_flops(self.h))
+
+    def flops_by_level(self):
+        a = [np.zeros(self.levels) for _ in range(4)]
+        self.L.chol_flops_by_level(self.h, *[_p(x) for x in a])
+        return dict(potrf=a[0], trsm=a[1], syrk=a[2], gemm=a[3])
+
+    def call_counts(self):
+        c = np.zeros(4, dtype=np.int64)
+        self.L.chol_call_counts(self.h, _p(c))
+        return dict(potrf=int(c[0]), trsm=int(c[1]), syrk=int(c[2]), gemm=int(c[3]))
+
+    def factor_doubles(self):
+        return int(self.L.chol_factor_doubles(self.h))
+
+    # ---- numeric (mmat.rg:1211-1358), GPU only
+    def assemble(self):
+        self._ck(self.L.chol_assemble(self.h))
+
+    def factor(self, iterations=1, warmup=0):
+        st = _lib.Stats()
+        self._ck(self.L.chol_factor(self.h, iterations, warmup, C.byref(st)))
+        return st
+
+    def fused_dpotrf(self, lvl):
+        self._ck(self.L.chol_fused_dpotrf(self.h, lvl))
+
+    def fused_dtrsm(self, lvl):
+        self._ck(self.L.chol_fused_dtrsm(self.h, lvl))
+
+    def fused_update(self, lvl):
+        self._ck(self.L.chol_fused_update(self.h, lvl))
+
+    def factor_host(self, values=None):
+        """end to end with host buffers: H2D of A's values, assemble, factor, D2H of diag(L)"""
+        st = _lib.Stats()
+        diag = np.zeros(self.n, dtype=np.float64)
+        if values is None:
+            self._ck(self.L.chol_factor_host(self.h, None, C.c_int64(0), _p(diag), C.byref(st)))
+        else:
+            v = np.ascontiguousarray(values, dtype=np.float64)
+            self._ck(self.L.chol_factor_host(self.h, _p(v), C.c_int64(v.size), _p(diag), C.byref(st)))
+        return diag, st
+
+    def kernel_times(self):
+        a, b, c, f = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.chol_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
+        return dict(potrf_ms=a.value, trsm_ms=b.value, gemm_ms=c.value, gemm_flops=f.value)
+
+    # ---- results (mmat.rg:1360-1362)
+    def factor_nnz(self):
+        k = int(self.L.chol_factor_nnz(self.h))
+        if k < 0:
+            raise CholeskyError(self.L.chol_last_error(self.h).decode())
+        return k
+
+    def factor_coo(self):
+        k = self.factor_nnz()
+        I = np.zeros(k, dtype=np.int32)
+        J = np.zeros(k, dtype=np.int32)
+        V = np.zeros(k, dtype=np.float64)
+        self.L.chol_get_factor_coo(self.h, _p(I), _p(J), _p(V))
+        return I, J, V
+
+    def factor_dense(self):
+        out = np.zeros((self.n, self.n), dtype=np.float64)
+        self._ck(self.L.chol_get_factor_dense(self.h, _p(out)))
+        return out
+
+    def write_factor(self, path, full_precision=False):
+        self._ck(self.L.chol_write_factor(self.h, path.encode(), 1 if full_precision else 0))
+
+    def residual(self, k=16, seed=1):
+        r = C.c_double()
+        self._ck(self.L.chol_residual(self.h, k, C.c_uint64(seed), C.byref(r)))
+        return r.value
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+        x = np.zeros(self.n, dtype=np.float64)
+        self._ck(self.L.chol_solve(self.h, _p(b), _p(x)))
+        return x
+
+
+def read_vector(path, n):
+    out = np.zeros(n, dtype=np.float64)
+    if _lib.load().chol_read_vector(path.encode(), n, _p(out)) != 0:
+        raise CholeskyError("cannot read " + path)
+    return out
+
+
+def write_solution(path, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if _lib.load().chol_write_solution(path.encode(), x.size, _p(x)) != 0:
+        raise CholeskyError("cannot write " + path)

@@ -1,0 +1,119 @@
+/*
+ * cholesky.h -- C ABI of the B200-native sparse Cholesky numeric-factorization engine.
+ *
+ * Drop-in boundary for the hot path of syamajala/cholesky.  In the reference this file exports
+ * one symbol, `void register_mappers()` (cholesky.h:19-27, cholesky.cc:88-91), and the numeric
+ * path sits behind Terra FFI calls into CBLAS/LAPACKE issued by the fused leaf tasks
+ * (blas.rg:292-504) that the level loop launches (mmat.rg:1227-1355).  The entry points below
+ * replace exactly that: `chol_factor` is the level loop, `chol_fused_*` are the per-level fused
+ * leaf tasks, and the loaders/writers keep the reference's file formats (mmio.c, mnd.c,
+ * mmat.rg:102-147).  Plain pointers and sizes only; int return 0 = ok, <0 = error
+ * (chol_last_error gives the text).  Host pointers are borrowed; device memory is owned by the
+ * handle.  One host thread drives a handle; one handle drives one GPU.
+ */
+#ifndef __CHOLESKY_H__
+#define __CHOLESKY_H__
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chol chol_t;
+
+/* reference `fspace Filled` (blas.rg:55-61): Legion int1d/int2d/rect2d are 64-bit => 9 x int64.
+ * filled == 0 means structurally FILLED (mmat.rg:615, 1205-1206). */
+typedef struct {
+  int64_t filled, sep_x, sep_y, interval, cluster, lo_x, lo_y, hi_x, hi_y;
+} chol_filled_t;
+
+typedef struct {
+  double seconds_best, seconds_median, seconds_last; /* level loop only (mmat.rg:1226-1355 region) */
+  double assemble_seconds;                           /* fill_block equivalent (mmat.rg:1216-1224) */
+  double flops;                                      /* algorithmic flops of the reference BLAS call list */
+  int64_t kernel_launches;                           /* kernels launched per iteration in the timed region */
+  int info;                                          /* 0, or 1-based permuted column of a non-positive pivot */
+} chol_stats_t;
+
+/* ---- lifecycle.  replaces: regentlib.start(main, register_mappers) (mmat.rg:1498) */
+int chol_create(const int *devices, int ngpu, chol_t **out);
+void chol_destroy(chol_t *);
+const char *chol_last_error(chol_t *);
+void register_mappers(void); /* kept so that anything linking the old symbol still resolves; no-op */
+
+/* ---- inputs.  replaces: read_matrix_banner/read_separators/read_clusters/read_matrix
+ * (mmat.rg:76-100, 851-883 -> mmio.c:96-217, mnd.c:22-199) */
+int chol_load(chol_t *, const char *matrix_mtx, const char *separators_txt, const char *clusters_txt);
+/* same data from memory: lower-triangle coordinate entries (0-based, row >= col); separator dof
+ * lists concatenated in ascending separator id (sep_ptr has nsep+1 entries); cluster interval lists
+ * concatenated per separator per interval: iv_ptr has (total intervals + 1) entries, sep_iv_ptr has
+ * nsep+1 entries indexing iv_ptr. */
+int chol_load_arrays(chol_t *, int n, int64_t nz, const int32_t *I, const int32_t *J, const double *V, int levels,
+                     int nsep, const int64_t *sep_ptr, const int32_t *sep_dofs, const int64_t *sep_iv_ptr,
+                     const int64_t *iv_ptr, const int32_t *iv_vals);
+/* synthetic inputs of BASELINE.json: nx*ny*nz grid Laplacian, stencil 5 (2-D), 7 or 27 (3-D), dof
+ * index x + nx*(y + ny*z), geometric nested dissection to `levels` levels (0 = the utils.py:6-7
+ * rule ceil(log2(n/64))+1) with the cluster interval hierarchy of the reference's clust files. */
+int chol_generate(chol_t *, int nx, int ny, int nz, int stencil, int levels);
+/* dump the loaded/generated problem in the reference's three text formats (any path may be NULL) */
+int chol_write_inputs(chol_t *, const char *matrix_mtx, const char *separators_txt, const char *clusters_txt);
+
+/* ---- host symbolic analysis.  replaces: build_separator_tree, partition_matrix,
+ * find_index_space_2d/3d, fill_block's flags, compute_filled_clusters (mmat.rg:299-1028).
+ * keep_records != 0 keeps every Filled record for chol_get_filled (counts and checksums are
+ * always kept). */
+int chol_analyze(chol_t *, int keep_records);
+int chol_n(chol_t *);
+int64_t chol_nz(chol_t *);
+int chol_levels(chol_t *);
+int chol_num_separators(chol_t *);
+int chol_max_int_size(chol_t *);
+int64_t chol_num_blocks(chol_t *);
+int64_t chol_num_clusters0(chol_t *);
+int chol_get_perm(chol_t *, int32_t *perm);                 /* permuted row -> original dof */
+int chol_get_sep_sizes(chol_t *, int32_t *sizes_by_label);  /* nsep entries */
+int64_t chol_get_block_bounds(chol_t *, int64_t *out6);     /* (row_sep, col_sep, lo_x, lo_y, hi_x, hi_y) */
+int64_t chol_num_filled(chol_t *, int interval_lbl);
+int64_t chol_get_filled(chol_t *, int interval_lbl, chol_filled_t *out); /* sorted (sep_x, sep_y, cluster) */
+uint64_t chol_filled_checksum(chol_t *, int interval_lbl);  /* order independent, same hash as the oracle */
+double chol_flops(chol_t *);
+int chol_flops_by_level(chol_t *, double *potrf, double *trsm, double *syrk, double *gemm);
+int chol_call_counts(chol_t *, int64_t *c4);                /* reference BLAS calls: potrf, trsm, syrk, gemm */
+int64_t chol_factor_doubles(chol_t *);                      /* device doubles of factor storage */
+
+/* ---- numeric factorization on the GPU.  replaces: the level loop mmat.rg:1211-1358 and the
+ * fused leaf tasks blas.rg:292-504.  chol_factor = `iterations` x (assemble; level loop), timing
+ * the level loop with CUDA events on the launching stream (warmup iterations run first, untimed). */
+int chol_assemble(chol_t *);
+int chol_factor(chol_t *, int iterations, int warmup, chol_stats_t *stats);
+/* piecewise: one tree level, one phase -- mirror fused_dpotrf / fused_dtrsm / fused_dsyrk+dgemm */
+int chol_fused_dpotrf(chol_t *, int lvl);
+int chol_fused_dtrsm(chol_t *, int lvl);
+int chol_fused_update(chol_t *, int lvl);
+/* end to end with HOST buffers: upload A's values (in the order given at load time), assemble,
+ * factor, and read back diag(L) in permuted order.  values may be NULL (reuse the loaded ones). */
+int chol_factor_host(chol_t *, const double *values, int64_t nz, double *diag_out, chol_stats_t *stats);
+int chol_synchronize(chol_t *);
+/* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
+int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops);
+
+/* ---- results.  replaces: write_matrix (mmat.rg:102-147) */
+int64_t chol_factor_nnz(chol_t *);                                           /* entries != 0 */
+int64_t chol_get_factor_coo(chol_t *, int32_t *I, int32_t *J, double *V);   /* 0-based permuted */
+int chol_get_factor_dense(chol_t *, double *out_row_major_nxn);             /* small n only */
+int chol_write_factor(chol_t *, const char *path, int full_precision);     /* "%0.8g" or "%.17g" */
+/* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F, W = k Rademacher columns (seeded) */
+int chol_residual(chol_t *, int k, uint64_t seed, double *rel);
+
+/* ---- solve (next row f-1).  replaces: mmat.rg:1364-1495, blas.rg:217-290, mnd.c:201-229 */
+int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out */
+int chol_read_vector(const char *path, int n, double *out);
+int chol_write_solution(const char *path, int n, const double *x);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* __CHOLESKY_H__ */

@@ -1,0 +1,146 @@
+"""GPU parity tests: the CUDA numeric factorization (through the C ABI) against the pinned CPU
+oracle and the golden vectors of the reference's verify.py.  Tolerances (BASELINE.json north_star):
+factor entries within 1e-10 relative with an absolute floor (conftest.entrywise_ok), relative
+residual <= 1e-12, pattern bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import CASES, entrywise_ok
+from cholesky_b200 import Cholesky, read_vector
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _coo_dict(I, J, V):
+    return {(int(i), int(j)): float(v) for i, j, v in zip(I, J, V)}
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_factor_matches_oracle_and_golden(case, golden):
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze(keep_records=True)
+    st = ch.factor()
+    assert st.info == 0 and st.kernel_launches > 0
+    o = orc.Oracle(g.mtx, g.ord, g.clust)
+    o.factor(threads=1)
+    L, Lo, Lg = ch.factor_dense(), o.factor_dense(), g.L_dense()
+    ok, worst = entrywise_ok(L, Lo)
+    assert ok, f"vs oracle {worst}"
+    ok, worst = entrywise_ok(L, Lg)
+    assert ok, f"vs scipy golden {worst}"
+    # identical structural nonzeros
+    assert ch.factor_nnz() == g.struct["nnzL"]
+    I, J, _ = ch.factor_coo()
+    Io, Jo, _ = o.factor_coo()
+    assert set(zip(I.tolist(), J.tolist())) == set(zip(Io.tolist(), Jo.tolist()))
+    A = g.pmat_dense()
+    A = A + np.tril(A, -1).T
+    assert np.linalg.norm(A - L @ L.T) / np.linalg.norm(A) <= 1e-12
+    assert ch.residual(k=8) <= 1e-12
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_reference_acceptance_checks(case, golden, tmp_path):
+    """what test_matrices.py asserts: check_matrix on the written factor and check_solution, both 1e-4"""
+    import scipy.io
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    ch.factor()
+    p = str(tmp_path / "factor.mtx")
+    ch.write_factor(p)
+    L = np.tril(np.asarray(scipy.io.mmread(p).todense()))
+    assert np.allclose(g.L_dense(), L, rtol=1e-4, atol=1e-4)
+    x = ch.solve(read_vector(g.b, g.n))
+    assert np.allclose(x, g.x, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["lapl_400x400", "lapl_3375x3375"])
+def test_piecewise_fused_tasks_match_oracle(case, golden):
+    """level by level, phase by phase: fused_dpotrf / fused_dtrsm / fused_dsyrk+dgemm"""
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    o = orc.Oracle(g.mtx, g.ord, g.clust)
+    ch.assemble()
+    o.assemble()
+    np.testing.assert_array_equal(ch.factor_dense(), o.factor_dense())  # assembly is exact
+    for lvl in range(ch.levels - 1, -1, -1):
+        for step in ("fused_dpotrf", "fused_dtrsm", "fused_update"):
+            getattr(ch, step)(lvl)
+            getattr(o, step)(lvl)
+            ok, worst = entrywise_ok(ch.factor_dense(), o.factor_dense())
+            assert ok, f"level {lvl} {step}: {worst}"
+
+
+@pytest.mark.parametrize("grid", [(16, 16, 16, 7, 0), (33, 17, 1, 5, 0), (12, 12, 12, 27, 0), (24, 20, 9, 7, 6),
+                                  (40, 40, 1, 5, 3), (30, 30, 30, 7, 4)])
+def test_generated_grids_match_oracle(grid, tmp_path):
+    ch = Cholesky().generate(*grid)
+    m, o_, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch.write_inputs(m, o_, c)
+    ch.analyze()
+    ch.factor()
+    o = orc.Oracle(m, o_, c)
+    o.factor(threads=2)
+    I, J, V = ch.factor_coo()
+    Io, Jo, Vo = o.factor_coo()
+    a, b = _coo_dict(I, J, V), _coo_dict(Io, Jo, Vo)
+    assert a.keys() == b.keys()
+    ref = np.array([b[k] for k in a])
+    got = np.array([a[k] for k in a])
+    scale = np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max())
+    assert np.max(np.abs(got - ref) / scale) <= 1e-10
+    assert ch.residual(k=8) <= 1e-12
+
+
+def test_large_front_blocking_paths(tmp_path):
+    """a 2-level tree over a 40x40x40 grid has a 1600-dof root: exercises the left-looking outer
+    blocks (NBO) and the odd-sized last tile"""
+    ch = Cholesky().generate(41, 40, 39, 7, 2).analyze()
+    ch.factor()
+    assert ch.residual(k=4) <= 1e-12
+
+
+def test_idempotent_and_deterministic(golden):
+    g = golden["lapl_3375x3375"]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    ch.factor()
+    a = ch.factor_coo()
+    ch.factor(iterations=2)
+    b = ch.factor_coo()
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)  # bit-identical run to run (atomic-free accumulation)
+
+
+def test_end_to_end_host_call(golden):
+    g = golden["lapl_3375x3375"]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    diag, st = ch.factor_host()
+    Ld = np.diag(g.L_dense())
+    assert np.allclose(diag, Ld, rtol=1e-10, atol=0)
+
+
+def test_not_positive_definite_is_reported(golden, tmp_path):
+    from cholesky_b200 import CholeskyError
+    g = golden["lapl_25x25"]
+    bad = tmp_path / "neg.mtx"
+    bad.write_text(open(g.mtx).read().replace("1 1 4.0", "1 1 -4.0", 1))
+    ch = Cholesky().load(str(bad), g.ord, g.clust).analyze()
+    with pytest.raises(CholeskyError, match="not positive definite"):
+        ch.factor()
+
+
+def test_config2_512x512_properties():
+    """BASELINE config 2 at full size through size-independent properties"""
+    ch = Cholesky().generate(512, 512, 1, 5, 0).analyze()
+    st = ch.factor()
+    assert st.info == 0
+    assert ch.residual(k=4) <= 1e-12
+
+
+def test_config3_64cubed_properties():
+    """BASELINE config 3 at full size: residual estimator + solve round trip"""
+    ch = Cholesky().generate(64, 64, 64, 7, 0).analyze()
+    st = ch.factor()
+    assert st.info == 0
+    assert ch.residual(k=2) <= 1e-12

@@ -1,0 +1,123 @@
+"""CPU tests of the product's host side: file readers, generators, symbolic analysis and schedule
+compiler, compared bit for bit with the pinned oracle.  No compute calls on a GPU here."""
+import ctypes as C
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES
+from cholesky_b200 import Cholesky, CholeskyError, _lib
+from oracle import oracle as orc
+
+GRIDS = [(15, 15, 15, 7, 5), (16, 16, 16, 7, 0), (33, 17, 1, 5, 0), (12, 12, 12, 27, 0), (24, 20, 9, 7, 6)]
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    for name in _lib.EXPORTS:
+        assert hasattr(L, name), name
+    # and the headers declare nothing that is not exported
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import re
+    declared = set()
+    for h in ("cholesky.h", "chol_mmio.h", "chol_mnd.h"):
+        src = open(os.path.join(root, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b((?:chol|mm|mnd)_[a-z0-9_]+|register_mappers)\s*\(", src))
+    declared = {d for d in declared if not d.startswith(("mm_is_", "mm_set_", "mm_clear", "mm_initialize"))}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_symbolic_matches_oracle_on_reference_fixtures(case, golden):
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze(keep_records=True)
+    o = orc.Oracle(g.mtx, g.ord, g.clust)
+    s = g.struct
+    assert (ch.n, ch.nz, ch.levels, ch.num_separators) == (s["n"], s["nz"], s["levels"], s["nsep"])
+    assert ch.num_blocks() == s["blocks"] and ch.num_clusters0() == s["clusters0"]
+    assert [ch.num_filled(t) for t in range(ch.levels)] == s["filled"]
+    assert ch.call_counts() == s["calls"]
+    np.testing.assert_array_equal(ch.perm(), o.perm())
+    np.testing.assert_array_equal(ch.sep_sizes(), o.sep_sizes())
+    np.testing.assert_array_equal(ch.block_bounds(), o.block_bounds())
+    assert ch.max_int_size() == o.max_int_size()
+    for t in range(ch.levels):
+        np.testing.assert_array_equal(ch.filled(t), o.filled(t))
+        assert ch.filled_checksum(t) == o.filled_checksum(t)
+    assert ch.flops() == o.flops()
+    fa, fb = ch.flops_by_level(), o.flops_by_level()
+    for k in fa:
+        np.testing.assert_array_equal(fa[k], fb[k])
+
+
+@pytest.mark.parametrize("grid,name", [((3, 3, 1, 5, 2), "lapl_9x9"), ((5, 5, 1, 5, 3), "lapl_25x25"),
+                                       ((20, 20, 1, 5, 5), "lapl_400x400"), ((15, 15, 15, 7, 5), "lapl_3375x3375")])
+def test_generated_laplacian_is_byte_identical_to_fixture(grid, name, golden, tmp_path):
+    ch = Cholesky().generate(*grid)
+    m = str(tmp_path / "a.mtx")
+    ch.write_inputs(m, None, None)
+    assert filecmp.cmp(m, golden[name].mtx, shallow=False)
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+def test_generated_nd_files_roundtrip_and_match_oracle(grid, tmp_path):
+    ch = Cholesky().generate(*grid)
+    m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch.write_inputs(m, o, c)
+    ch.analyze(keep_records=True)
+    ch2 = Cholesky().load(m, o, c).analyze(keep_records=True)   # through the text readers
+    oc = orc.Oracle(m, o, c)
+    assert ch.levels == oc.levels and ch.num_separators == oc.num_separators
+    np.testing.assert_array_equal(ch.perm(), oc.perm())
+    np.testing.assert_array_equal(ch2.perm(), oc.perm())
+    for t in range(ch.levels):
+        np.testing.assert_array_equal(ch.filled(t), oc.filled(t))
+        np.testing.assert_array_equal(ch2.filled(t), oc.filled(t))
+        assert ch.filled_checksum(t) == oc.filled_checksum(t)
+    assert ch.call_counts() == oc.call_counts()
+    assert ch.flops() == oc.flops()
+    # separators are true vertex separators: nothing of A is dropped
+    oc.assemble()
+    assert oc.factor_nnz() == ch.nz
+
+
+def test_levels_rule_matches_utils_py():
+    import math
+    for dims, st in [((512, 512, 1), 5), ((64, 64, 64), 7)]:
+        ch = Cholesky().generate(*dims, st, 0).analyze()
+        n = dims[0] * dims[1] * dims[2]
+        assert ch.levels == math.ceil(math.log(n / 64) / math.log(2)) + 1  # utils.py:6-7
+
+
+def test_bad_inputs_are_reported(golden, tmp_path):
+    g = golden["lapl_25x25"]
+    with pytest.raises(CholeskyError):
+        Cholesky().load(str(tmp_path / "missing.mtx"), g.ord, g.clust)
+    bad = tmp_path / "bad_ord.txt"
+    bad.write_text(open(g.ord).read().replace("6;6,10,12,14,18,", "6;6,10,12,14,"))
+    with pytest.raises(CholeskyError):
+        Cholesky().load(g.mtx, str(bad), g.clust)
+    # a separator with two clusters at elimination breaks the reference's fused tasks
+    badc = tmp_path / "bad_clust.txt"
+    badc.write_text(open(g.clust).read().replace("0;0,4,;", "0;0,2,4,;"))
+    with pytest.raises(CholeskyError):
+        Cholesky().load(g.mtx, g.ord, str(badc)).analyze()
+
+
+def test_hash_sax_matches_oracle():
+    L = _lib.load()
+    for k in (0, 1, 24, 3375 * 3374 + 17, 2**40 + 12345):
+        assert int(L.mnd_hash_sax(C.c_uint64(k))) == orc.hash_sax(k)
+
+
+def test_numeric_path_fails_loudly_without_gpu(golden):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = golden["lapl_9x9"]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    with pytest.raises(CholeskyError, match="no CUDA device"):
+        ch.factor()
