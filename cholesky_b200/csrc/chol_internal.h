@@ -110,6 +110,7 @@ struct Launch {
   int phase;
   int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
+  int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128
 };
 
 struct Schedule {
@@ -122,7 +123,8 @@ struct Schedule {
   std::vector<Launch> launches;
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
   std::vector<int64_t> a_off;
-  int nb = 64, nbo = 256, bm = 64, bn = 64, slab = 64;
+  int nb = 64, nbo = 256, slab = 128;
+  int big_m = 192, big_n = 128;  // problems at least this large use the 128x128 tile configuration
 };
 
 int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string &err);

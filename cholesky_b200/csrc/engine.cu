@@ -18,6 +18,7 @@
 using namespace chb;
 
 typedef GemmCfg<64, 64, 16, 32, 32, 3> Gemm64;
+typedef GemmCfg<128, 128, 16, 64, 32, 4> Gemm128;
 
 struct chol {
   std::string err;
@@ -239,6 +240,7 @@ static int ensure_device(chol_t *c) {
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
   CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
   return 0;
 }
 
@@ -262,11 +264,15 @@ static int run_launch(chol_t *c, const Launch &l) {
       potrf_tile<<<(unsigned)l.count, 256, 0, c->stream>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
-      trsm_tile<<<(unsigned)l.count, 64, 0, c->stream>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      trsm_tile<<<(unsigned)l.count, kSlab, 0, c->stream>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
-      gemm_grouped<64, 64, 16, 32, 32, 3><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
-          c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
+      if (l.cfg == 1)
+        gemm_grouped<128, 128, 16, 64, 32, 4><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
+            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
+      else
+        gemm_grouped<64, 64, 16, 32, 32, 3><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
+            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
       break;
   }
   return 0;
@@ -406,6 +412,14 @@ int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_o
     st->info = info;
   }
   if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  return 0;
+}
+
+int64_t chol_num_launches(chol_t *c) { return c->analyzed ? (int64_t)c->D.launches.size() : -1; }
+int chol_get_launch(chol_t *c, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg) {
+  if (!c->analyzed || i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
+  const Launch &l = c->D.launches[i];
+  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg;
   return 0;
 }
 

@@ -146,9 +146,18 @@ __global__ void __launch_bounds__(256) potrf_tile(const PotrfDesc *__restrict__ 
   const PotrfDesc d = descs[blockIdx.x];
   double *__restrict__ A = fac + d.off;
   const int nb = d.nb, tid = threadIdx.x;
-  for (int i = tid; i < nb * nb; i += 256) {
-    int r = i % nb, c = i / nb;
-    T[r][c] = (r >= c) ? A[r + (size_t)c * d.ld] : 0.0;
+  {  // all 16 loads of a thread in flight at once (independent, predicated)
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      int i = tid + u * 256, r = i % kNB, c = i / kNB;
+      v[u] = (r < nb && c < nb && r >= c) ? A[r + (size_t)c * d.ld] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      int i = tid + u * 256;
+      T[i % kNB][i / kNB] = v[u];
+    }
   }
   __syncthreads();
   for (int k = 0; k < nb; k++) {
@@ -162,42 +171,56 @@ __global__ void __launch_bounds__(256) potrf_tile(const PotrfDesc *__restrict__ 
     }
     __syncthreads();
     const double dk = T[k][k];
-    for (int i = k + 1 + tid; i < nb; i += 256) T[i][k] /= dk;
+    if (tid > k && tid < nb) T[tid][k] /= dk;
     __syncthreads();
-    const int rem = nb - k - 1;
-    for (int idx = tid; idx < rem * rem; idx += 256) {
-      int i = k + 1 + idx % rem, j = k + 1 + idx / rem;
-      if (i >= j) T[i][j] -= T[i][k] * T[j][k];
+    // trailing update of the lower triangle: thread (ti, tj) strides over rows / columns
+    const int ti = tid & 15, tj = tid >> 4;
+    for (int j = k + 1 + tj; j < nb; j += 16) {
+      const double ljk = T[j][k];
+      for (int i = j + ti; i < nb; i += 16) T[i][j] -= T[i][k] * ljk;
     }
     __syncthreads();
   }
-  for (int i = tid; i < nb * nb; i += 256) {
-    int r = i % nb, c = i / nb;
-    if (r >= c) A[r + (size_t)c * d.ld] = T[r][c];
+#pragma unroll
+  for (int u = 0; u < 16; u++) {
+    int i = tid + u * 256, r = i % kNB, c = i / kNB;
+    if (r < nb && c < nb && r >= c) A[r + (size_t)c * d.ld] = T[r][c];
   }
 }
 
-__global__ void __launch_bounds__(64) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
-                                                double *__restrict__ fac) {
+// 128-row slab per CTA, one row per thread.  L (nb x nb) is staged into shared memory with all of a
+// thread's loads in flight; the row lives in registers and is solved by forward substitution.
+constexpr int kSlab = 128;
+__global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
+                                                   double *__restrict__ fac) {
   __shared__ double Ls[kNB][kNB + 1];  // Ls[c][k] = L[c][k]
   const TileRef tl = tiles[blockIdx.x];
   const TrsmDesc d = descs[tl.prob];
   const int slab = (int)tl.tr | ((int)tl.tc << 16);
   const int tid = threadIdx.x, nb = d.nb;
   const double *__restrict__ Lg = fac + d.l_off;
-  for (int i = tid; i < kNB * kNB; i += 64) {
-    int r = i % kNB, c = i / kNB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < nb && c < nb && r >= c) v = Lg[r + (size_t)c * d.ld];
-    Ls[r][c] = v;
-  }
-  __syncthreads();
-  const int row = slab * 64 + tid;
-  if (row >= d.rows) return;
-  double *__restrict__ Bp = fac + d.b_off + row;
+  const int row = slab * kSlab + tid;
+  const bool live = row < d.rows;
+  double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
   double x[kNB];
 #pragma unroll
-  for (int c = 0; c < kNB; c++) x[c] = (c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+  for (int c = 0; c < kNB; c++) x[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+  {
+    constexpr int PER = kNB * kNB / kSlab;
+    double v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
+      v[u] = (r < nb && c < nb && r >= c) ? Lg[r + (size_t)c * d.ld] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      int i = tid + u * kSlab;
+      Ls[i % kNB][i / kNB] = v[u];
+    }
+  }
+  __syncthreads();
+  if (!live) return;
 #pragma unroll
   for (int c = 0; c < kNB; c++) {
     double s = x[c];

@@ -26,12 +26,14 @@ struct Builder {
   Schedule &D;
   Builder(const Problem &p, const Symbolic &s, Schedule &d) : P(p), S(s), D(d) {}
 
-  int64_t gemm_begin = 0;
-  double gemm_flops = 0;
+  // tiles of the launch being built, per tile configuration (0: 64x64, 1: 128x128)
+  std::vector<TileRef> cur[2];
+  double cur_flops[2] = {0, 0};
   void begin_gemm() {
-    gemm_begin = (int64_t)D.tiles.size();
-    gemm_flops = 0;
+    cur[0].clear(), cur[1].clear();
+    cur_flops[0] = cur_flops[1] = 0;
   }
+  int cfg_of(const GemmProblem &g) const { return (g.M >= D.big_m && g.N >= D.big_n) ? 1 : 0; }
   // one problem with a single contributor (in-panel updates)
   void add_problem(int64_t c_off, int ldc, int M, int N, int tri, int64_t a_off, int64_t b_off, int lda, int ldb, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return;
@@ -40,21 +42,26 @@ struct Builder {
     g.contrib_begin = (int)D.contribs.size(), g.contrib_count = 1;
     D.contribs.push_back(GemmContrib{a_off, b_off, lda, ldb, K, 0});
     D.probs.push_back(g);
-    add_tiles((int)D.probs.size() - 1);
-    gemm_flops += (tri ? 1.0 : 2.0) * M * N * K;
+    add_tiles((int)D.probs.size() - 1, (tri ? 1.0 : 2.0) * M * N * K);
   }
-  void add_tiles(int prob) {
+  void add_tiles(int prob, double flops) {
     const GemmProblem &g = D.probs[prob];
-    int tr_n = (g.M + D.bm - 1) / D.bm, tc_n = (g.N + D.bn - 1) / D.bn;
+    const int cfg = cfg_of(g), bm = cfg ? 128 : 64, bn = bm;
+    int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
     for (int tc = 0; tc < tc_n; tc++)
       for (int tr = 0; tr < tr_n; tr++) {
-        if (g.tri && (tr + 1) * D.bm - 1 < tc * D.bn) continue;  // wholly above the diagonal
-        D.tiles.push_back(TileRef{prob, (uint16_t)tr, (uint16_t)tc});
+        if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
+        cur[cfg].push_back(TileRef{prob, (uint16_t)tr, (uint16_t)tc});
       }
+    cur_flops[cfg] += flops;
   }
   void end_gemm(int level, int phase) {
-    int64_t cnt = (int64_t)D.tiles.size() - gemm_begin;
-    if (cnt > 0) D.launches.push_back(Launch{K_GEMM, level, phase, gemm_begin, cnt, gemm_flops});
+    for (int cfg = 1; cfg >= 0; cfg--) {
+      if (cur[cfg].empty()) continue;
+      int64_t b = (int64_t)D.tiles.size();
+      D.tiles.insert(D.tiles.end(), cur[cfg].begin(), cur[cfg].end());
+      D.launches.push_back(Launch{K_GEMM, level, phase, b, (int64_t)cur[cfg].size(), cur_flops[cfg], cfg});
+    }
   }
 };
 
@@ -149,7 +156,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
               if (n <= d0) continue;
               D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
             }
-            if ((int64_t)D.potrf.size() > b) D.launches.push_back(Launch{K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0});
+            if ((int64_t)D.potrf.size() > b) D.launches.push_back(Launch{K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0});
           }
           {
             int64_t b = (int64_t)D.trsm_tiles.size();
@@ -164,7 +171,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
               int ns = (rend - rbeg + SLAB - 1) / SLAB;
               for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
             }
-            if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0});
+            if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0});
           }
           // right-looking update of the rest of this outer block column
           B.begin_gemm();
@@ -222,13 +229,14 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
       g.c_off = S.poff[q.p] + q.crow + (int64_t)q.ccol * S.ld[q.p];
       g.ldc = S.ld[q.p], g.M = q.M, g.N = q.N, g.tri = q.tri;
       g.contrib_begin = (int)D.contribs.size(), g.contrib_count = (int)(j - i);
+      double pf = 0;
       for (size_t c = i; c < j; c++) {
         if (pairs[c].M != q.M || pairs[c].N != q.N || pairs[c].tri != q.tri) return err = "internal: contributors of one destination cluster disagree on its shape", -1;
         D.contribs.push_back(GemmContrib{pairs[c].a_off, pairs[c].b_off, pairs[c].ld, pairs[c].ld, pairs[c].K, 0});
-        B.gemm_flops += (q.tri ? 1.0 : 2.0) * q.M * q.N * pairs[c].K;
+        pf += (q.tri ? 1.0 : 2.0) * q.M * q.N * pairs[c].K;
       }
       D.probs.push_back(g);
-      B.add_tiles((int)D.probs.size() - 1);
+      B.add_tiles((int)D.probs.size() - 1, pf);
       i = j;
     }
     B.end_gemm(lvl, PH_UPDATE);

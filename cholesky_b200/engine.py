@@ -152,6 +152,18 @@ class Cholesky:
         self._ck(self.L.chol_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
         return dict(potrf_ms=a.value, trsm_ms=b.value, gemm_ms=c.value, gemm_flops=f.value)
 
+    def launches(self):
+        """the compiled launch list as dicts (kind, level, phase, ctas, flops, cfg)"""
+        out = []
+        kind, level, phase, cfg = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ctas, flops = C.c_int64(), C.c_double()
+        for i in range(int(self.L.chol_num_launches(self.h))):
+            self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
+                                   C.byref(ctas), C.byref(flops), C.byref(cfg))
+            out.append(dict(kind=("potrf_tile", "trsm_tile", "gemm_grouped")[kind.value], level=level.value,
+                            phase=phase.value, ctas=ctas.value, flops=flops.value, cfg=cfg.value))
+        return out
+
     # ---- results (mmat.rg:1360-1362)
     def factor_nnz(self):
         k = int(self.L.chol_factor_nnz(self.h))

@@ -96,6 +96,10 @@ int chol_fused_update(chol_t *, int lvl);
  * factor, and read back diag(L) in permuted order.  values may be NULL (reuse the loaded ones). */
 int chol_factor_host(chol_t *, const double *values, int64_t nz, double *diag_out, chol_stats_t *stats);
 int chol_synchronize(chol_t *);
+/* the compiled launch list: kind 0 potrf_tile / 1 trsm_tile / 2 gemm_grouped, tree level, phase
+ * (1 fused_dpotrf, 2 fused_dtrsm, 4 fused_dsyrk+dgemm), CTAs, executed flops, tile configuration */
+int64_t chol_num_launches(chol_t *);
+int chol_get_launch(chol_t *, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg);
 /* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
 int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops);
 

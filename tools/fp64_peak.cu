@@ -68,6 +68,7 @@ double run(const char *name, double flop_per_warp_instr, int warps_per_block, do
 }
 
 int main() {
+  setvbuf(stdout, NULL, _IONBF, 0);
   double *d;
   cudaMalloc(&d, 148 * 4 * 1024 * sizeof(double));
   for (int w : {4, 8, 16}) {
@@ -79,7 +80,7 @@ int main() {
   }
   // cuBLAS DGEMM yardstick
   cublasHandle_t h;
-  cublasCreate(&h);
+  if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) { printf("cublasCreate failed\n"); return 1; }
   for (int n : {4096, 8192}) {
     double *A, *B, *C;
     size_t bytes = (size_t)n * n * sizeof(double);
