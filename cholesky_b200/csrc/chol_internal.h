@@ -102,7 +102,7 @@ struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
   int ld, nb, rows, pad;
 };
 
-enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2 };
+enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_BARRIER = 3, K_ALLREDUCE = 4 };
 enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
 struct Launch {
   int kind;
@@ -111,6 +111,7 @@ struct Launch {
   int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
   int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128
+  int shared;            // multi-GPU: this rank runs a slice of the tiles and stores into every rank's copy
 };
 
 struct Schedule {
@@ -124,10 +125,15 @@ struct Schedule {
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
   std::vector<int64_t> a_off;
   int nb = 64, nbo = 256, slab = 128;
-  int big_m = 192, big_n = 128;  // problems at least this large use the 128x128 tile configuration
+  int big_m = 192, big_n = 128;  // problems at least this large may use the 128x128 tile configuration ...
+  int min_tiles_128 = 296;       // ... when the launch then still has two waves of CTAs (2 x 148 SMs)
+  // multi-GPU partition (world = 2^depth ranks)
+  int rank = 0, world = 1, depth = 0;
+  int64_t top_doubles = 0;         // leading part of the factor buffer that holds the shared top panels
+  double shared_min_flops = 2e9;   // top-level GEMM launches at least this large are split across ranks
 };
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string &err);
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, std::string &err);
 
 uint64_t mix64(uint64_t x);
 uint64_t filled_hash(const FilledRec &r);

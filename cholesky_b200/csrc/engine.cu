@@ -44,8 +44,15 @@ struct chol {
   size_t h_pinned_bytes = 0;
   std::vector<double> h_fac;  // host copy of the factor, fetched lazily
   bool h_fac_valid = false;
-  double k_ms[3] = {0, 0, 0};
+  double k_ms[5] = {0, 0, 0, 0, 0};
   double k_gemm_flops = 0;
+  // multi-GPU: one handle per rank; peers' factor buffers and flag words mapped through CUDA IPC
+  int rank = 0, world = 1;
+  Peers peers = {};
+  unsigned long long *d_flags = nullptr;
+  unsigned long long epoch = 0;
+  bool peers_ready = false;
+  std::vector<void *> ipc_opened;
 };
 
 #define CK(call)                                                                                  \
@@ -80,7 +87,12 @@ static void free_device(chol_t *c) {
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
   cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_info);
   cudaFree(c->d_diag_off), cudaFree(c->d_diag);
+  for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  c->ipc_opened.clear();
+  cudaFree(c->d_flags);
+  c->d_flags = nullptr, c->peers_ready = false;
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->h_pinned = nullptr, c->h_pinned_bytes = 0;
   if (c->stream) cudaStreamDestroy(c->stream);
   c->device_ready = false;
 }
@@ -145,7 +157,7 @@ int chol_analyze(chol_t *c, int keep_records) {
   free_device(c);
   c->analyzed = false;
   if (analyze(c->P, c->S, keep_records != 0, c->err)) return -1;
-  if (build_schedule(c->P, c->S, c->D, c->err)) return -1;
+  if (build_schedule(c->P, c->S, c->D, c->rank, c->world, c->err)) return -1;
   c->analyzed = true;
   c->assembled = false;
   c->h_fac_valid = false;
@@ -239,8 +251,16 @@ static int ensure_device(chol_t *c) {
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
-  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
-  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
+  CK(cudaMalloc((void **)&c->d_flags, kMaxPeers * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_flags, 0, kMaxPeers * sizeof(unsigned long long)));
+  c->peers.n = 1, c->peers.rank = 0;
+  c->peers.fac[0] = c->d_fac, c->peers.flags[0] = c->d_flags;
+  c->peers_ready = (c->world == 1);
+  c->epoch = 0;
   return 0;
 }
 
@@ -258,27 +278,51 @@ static int do_assemble(chol_t *c) {
   return 0;
 }
 
+static void launch_barrier(chol_t *c) {
+  c->epoch++;
+  peer_barrier<<<1, 32, 0, c->stream>>>(c->peers, c->epoch);
+}
+
 static int run_launch(chol_t *c, const Launch &l) {
   switch (l.kind) {
     case K_POTRF:
-      potrf_tile<<<(unsigned)l.count, 256, 0, c->stream>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      potrf_tile<<<(unsigned)l.count, kNB, 0, c->stream>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
       trsm_tile<<<(unsigned)l.count, kSlab, 0, c->stream>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
-      if (l.cfg == 1)
-        gemm_grouped<128, 128, 16, 64, 32, 4><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
-            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
-      else
-        gemm_grouped<64, 64, 16, 32, 32, 3><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
-            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
+      if (l.count <= 0) break;
+      if (l.shared) {
+        if (l.cfg == 1)
+          gemm_grouped<128, 128, 16, 64, 32, 4, true><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
+              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+        else
+          gemm_grouped<64, 64, 16, 32, 32, 3, true><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
+              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+      } else {
+        if (l.cfg == 1)
+          gemm_grouped<128, 128, 16, 64, 32, 4, false><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
+              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+        else
+          gemm_grouped<64, 64, 16, 32, 32, 3, false><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
+              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+      }
+      break;
+    case K_BARRIER:
+      launch_barrier(c);
+      break;
+    case K_ALLREDUCE:
+      launch_barrier(c);
+      allreduce_top<<<148 * 4, 256, 0, c->stream>>>(c->peers, l.count / 2);
+      launch_barrier(c);
       break;
   }
   return 0;
 }
 
 static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool per_kernel_timing) {
+  if (c->world > 1 && !c->peers_ready) return fail(c, "multi-GPU handle: exchange IPC handles first (chol_ipc_export / chol_ipc_import)");
   std::vector<cudaEvent_t> ev;
   std::vector<int> kinds;
   std::vector<double> fl;
@@ -297,7 +341,8 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   CK(cudaGetLastError());
   if (per_kernel_timing) {
     CK(cudaStreamSynchronize(c->stream));
-    c->k_ms[0] = c->k_ms[1] = c->k_ms[2] = 0, c->k_gemm_flops = 0;
+    for (double &m : c->k_ms) m = 0;
+    c->k_gemm_flops = 0;
     for (size_t i = 0; i < kinds.size(); i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
@@ -415,11 +460,63 @@ int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_o
   return 0;
 }
 
+/* ---- multi-GPU plumbing */
+int chol_set_partition(chol_t *c, int rank, int world) {
+  if (world < 1 || world > kMaxPeers || (world & (world - 1)) || rank < 0 || rank >= world) return fail(c, "world must be 1, 2, 4 or 8 and 0 <= rank < world");
+  c->rank = rank, c->world = world;
+  c->analyzed = false;
+  return 0;
+}
+int chol_ipc_export(chol_t *c, void *handles128) {
+  if (ensure_device(c)) return -1;
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], c->d_fac));
+  CK(cudaIpcGetMemHandle(&h[1], c->d_flags));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(handles128, h, 128);
+  return 0;
+}
+int chol_ipc_import(chol_t *c, const void *all_handles, int world) {
+  if (ensure_device(c)) return -1;
+  if (world != c->world) return fail(c, "world size mismatch");
+  const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
+  c->peers.n = world, c->peers.rank = c->rank;
+  for (int p = 0; p < world; p++) {
+    if (p == c->rank) {
+      c->peers.fac[p] = c->d_fac, c->peers.flags[p] = c->d_flags;
+      continue;
+    }
+    void *f = nullptr, *g = nullptr;
+    CK(cudaIpcOpenMemHandle(&f, h[2 * p], cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&g, h[2 * p + 1], cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(f), c->ipc_opened.push_back(g);
+    c->peers.fac[p] = (double *)f, c->peers.flags[p] = (unsigned long long *)g;
+  }
+  c->peers_ready = true;
+  return 0;
+}
+/* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
+ * [2] shared (tile-split) launches, [3] doubles of the shared top region, [4] potrf tiles, [5] trsm slabs */
+int chol_partition_stats(chol_t *c, double *out6) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  double a = 0, f = 0, sh = 0, pt = 0, ts = 0;
+  for (int64_t o : c->D.a_off) a += (o >= 0);
+  for (const Launch &l : c->D.launches) {
+    if (l.kind == K_GEMM) f += l.flops, sh += l.shared;
+    if (l.kind == K_POTRF) pt += (double)l.count;
+    if (l.kind == K_TRSM) ts += (double)l.count;
+  }
+  out6[0] = a, out6[1] = f, out6[2] = sh, out6[3] = (double)c->D.top_doubles, out6[4] = pt, out6[5] = ts;
+  return 0;
+}
+int chol_rank(chol_t *c) { return c->rank; }
+int chol_world(chol_t *c) { return c->world; }
+
 int64_t chol_num_launches(chol_t *c) { return c->analyzed ? (int64_t)c->D.launches.size() : -1; }
 int chol_get_launch(chol_t *c, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg) {
   if (!c->analyzed || i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
   const Launch &l = c->D.launches[i];
-  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg;
+  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg | (l.shared << 4);
   return 0;
 }
 
@@ -466,6 +563,10 @@ static void visit(chol_t *c, F fn) {
       for (int hc = hr << d; hc < ((hr + 1) << d); hc++) cols.push_back(hc);
     std::sort(cols.begin(), cols.end(), [](int a, int b) { return a > b; });  // ascending label
     for (int hc : cols) {
+      if (c->world > 1) {  // a rank reports its own subtree; rank 0 also the shared top panels
+        int lvc = P.level_of(hc), own = lvc < c->D.depth ? -1 : (hc >> (lvc - c->D.depth)) - (1 << c->D.depth);
+        if (!(own == c->rank || (own < 0 && c->rank == 0))) continue;
+      }
       const double *pan = c->h_fac.data() + S.poff[hc];
       int ld = S.ld[hc];
       for (int64_t s = S.seg_ptr[hc]; s < S.seg_ptr[hc + 1]; s++) {

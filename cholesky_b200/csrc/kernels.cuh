@@ -1,15 +1,20 @@
 // sm_100a kernels of the numeric factorization.  Three grouped kernels execute the whole level
-// schedule (see schedule.cc); one scatter kernel assembles A.
+// schedule (see schedule.cc); one scatter kernel assembles A; two small kernels carry the multi-GPU
+// exchange over NVLink peer memory.
 //
 //   gemm_grouped   C -= sum_c A_c B_c^T on FP64 tensor cores (mma.sync DMMA m8n8k4), operands
 //                  staged through shared memory by a multi-stage cp.async pipeline, one CTA per
 //                  destination tile, contributors accumulated in registers in a fixed order
 //                  (atomic-free, deterministic), lower-triangle masking for SYRK destinations.
+//                  SHARED variant: the tile is also stored into every peer's copy of the factor
+//                  (P2P stores), fusing the update with its broadcast.
 //                  Replaces cblas_dgemm / cblas_dsyrk as called at blas.rg:139-142, 187-189.
-//   potrf_tile     in-shared-memory Cholesky of one NB x NB pivot tile (LAPACKE_dpotrf, blas.rg:71).
-//   trsm_tile      one 64-row slab times L^-T by forward substitution, one row per thread
+//   potrf_tile     Cholesky of one NB x NB pivot tile, one row per thread in registers
+//                  (LAPACKE_dpotrf, blas.rg:71).
+//   trsm_tile      one 128-row slab times L^-T by forward substitution, one row per thread
 //                  (cblas_dtrsm Right/Lower/Trans/NonUnit, blas.rg:99-100).
 //   assemble       factor[a_off[e]] = value[e]   (fill_block, mmat.rg:529-633).
+//   peer_barrier / allreduce_top   cross-GPU barrier and sum of the ranks' top-panel copies.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,6 +22,13 @@
 #include "chol_internal.h"
 
 namespace chb {
+
+constexpr int kMaxPeers = 8;
+struct Peers {
+  double *fac[kMaxPeers];
+  unsigned long long *flags[kMaxPeers];
+  int n, rank;
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,10 +55,10 @@ struct GemmCfg {
   static constexpr int kSmemBytes = STAGES * kStageDoubles * 8;
 };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool SHARED>
 __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
     gemm_grouped(const GemmProblem *__restrict__ probs, const GemmContrib *__restrict__ contribs,
-                 const TileRef *__restrict__ tiles, double *__restrict__ fac) {
+                 const TileRef *__restrict__ tiles, double *__restrict__ fac, Peers peers) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES>;
   extern __shared__ __align__(16) double smem[];
   const TileRef tile = tiles[blockIdx.x];
@@ -130,70 +142,79 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
       for (int e = 0; e < 2; e++) {
         const int cc = col0 + wn0 + j * 8 + 2 * t + e;
         if (cc < pr.N && (!pr.tri || r >= cc)) {
-          double *p = C + r + (size_t)cc * pr.ldc;
-          *p -= acc[i][j][e];
+          const size_t o = r + (size_t)cc * pr.ldc;
+          const double v = C[o] - acc[i][j][e];
+          if (SHARED) {
+#pragma unroll
+            for (int p = 0; p < kMaxPeers; p++)
+              if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
+          } else
+            C[o] = v;
         }
       }
     }
   }
+  if (SHARED) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
-__global__ void __launch_bounds__(256) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac, int *__restrict__ info) {
-  __shared__ double T[kNB][kNB + 1];
+// One thread per row, the row in registers.  Column k: thread k finishes its diagonal entry and
+// publishes row k through shared memory; every thread below takes a dot product with it.
+__global__ void __launch_bounds__(kNB) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac, int *__restrict__ info) {
+  __shared__ double rowk[2][kNB + 2];
   const PotrfDesc d = descs[blockIdx.x];
   double *__restrict__ A = fac + d.off;
-  const int nb = d.nb, tid = threadIdx.x;
-  {  // all 16 loads of a thread in flight at once (independent, predicated)
-    double v[16];
+  const int nb = d.nb, i = threadIdx.x;
+  double a[kNB];
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      int i = tid + u * 256, r = i % kNB, c = i / kNB;
-      v[u] = (r < nb && c < nb && r >= c) ? A[r + (size_t)c * d.ld] : 0.0;
-    }
+  for (int c = 0; c < kNB; c++) a[c] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      int i = tid + u * 256;
-      T[i % kNB][i / kNB] = v[u];
-    }
-  }
-  __syncthreads();
-  for (int k = 0; k < nb; k++) {
-    if (tid == 0) {
-      double v = T[k][k];
-      if (!(v > 0.0)) {
-        atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-        v = 1.0;
+  for (int k = 0; k < kNB; k++) {
+    if (k < nb) {
+      double *rb = rowk[k & 1];
+      if (i == k) {
+        double s0 = a[k], s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int j = 0; j + 3 < k; j += 4) s0 -= a[j] * a[j], s1 -= a[j + 1] * a[j + 1], s2 -= a[j + 2] * a[j + 2], s3 -= a[j + 3] * a[j + 3];
+#pragma unroll
+        for (int j = k & ~3; j < k; j++) s0 -= a[j] * a[j];
+        double v = (s0 + s1) + (s2 + s3);
+        if (!(v > 0.0)) {
+          atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+          v = 1.0;
+        }
+        v = sqrt(v);
+        a[k] = v;
+#pragma unroll
+        for (int j = 0; j < k; j++) rb[j] = a[j];
+        rb[k] = v;
       }
-      T[k][k] = sqrt(v);
+      __syncthreads();
+      if (i > k) {
+        double s0 = a[k], s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int j = 0; j + 3 < k; j += 4) s0 -= a[j] * rb[j], s1 -= a[j + 1] * rb[j + 1], s2 -= a[j + 2] * rb[j + 2], s3 -= a[j + 3] * rb[j + 3];
+#pragma unroll
+        for (int j = k & ~3; j < k; j++) s0 -= a[j] * rb[j];
+        a[k] = ((s0 + s1) + (s2 + s3)) / rb[k];
+      }
     }
-    __syncthreads();
-    const double dk = T[k][k];
-    if (tid > k && tid < nb) T[tid][k] /= dk;
-    __syncthreads();
-    // trailing update of the lower triangle: thread (ti, tj) strides over rows / columns
-    const int ti = tid & 15, tj = tid >> 4;
-    for (int j = k + 1 + tj; j < nb; j += 16) {
-      const double ljk = T[j][k];
-      for (int i = j + ti; i < nb; i += 16) T[i][j] -= T[i][k] * ljk;
-    }
-    __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 16; u++) {
-    int i = tid + u * 256, r = i % kNB, c = i / kNB;
-    if (r < nb && c < nb && r >= c) A[r + (size_t)c * d.ld] = T[r][c];
-  }
+  for (int c = 0; c < kNB; c++)
+    if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = a[c];
 }
 
-// 128-row slab per CTA, one row per thread.  L (nb x nb) is staged into shared memory with all of a
-// thread's loads in flight; the row lives in registers and is solved by forward substitution.
+// 128-row slab per CTA, one row per thread in registers.  L^T is staged in shared memory so that
+// the eight multipliers a thread needs for one k are contiguous (broadcast vector loads); columns
+// are solved eight at a time to keep eight independent FMA chains in flight.
 constexpr int kSlab = 128;
 __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
                                                    double *__restrict__ fac) {
-  __shared__ double Ls[kNB][kNB + 1];  // Ls[c][k] = L[c][k]
+  __shared__ __align__(16) double Lt[kNB][kNB];  // Lt[k][c] = L[c][k]
+  __shared__ double rdiag[kNB];
   const TileRef tl = tiles[blockIdx.x];
   const TrsmDesc d = descs[tl.prob];
   const int slab = (int)tl.tr | ((int)tl.tc << 16);
@@ -215,18 +236,35 @@ __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ 
     }
 #pragma unroll
     for (int u = 0; u < PER; u++) {
-      int i = tid + u * kSlab;
-      Ls[i % kNB][i / kNB] = v[u];
+      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
+      Lt[c][r] = v[u];
+      if (r == c) rdiag[r] = 1.0 / v[u];
     }
   }
   __syncthreads();
   if (!live) return;
 #pragma unroll
-  for (int c = 0; c < kNB; c++) {
-    double s = x[c];
+  for (int cb = 0; cb < kNB; cb += 8) {
+    double s[8];
 #pragma unroll
-    for (int k = 0; k < c; k++) s -= x[k] * Ls[c][k];
-    x[c] = s / Ls[c][c];
+    for (int j = 0; j < 8; j++) s[j] = x[cb + j];
+#pragma unroll
+    for (int k = 0; k < cb; k++) {
+      const double xk = x[k];
+      const double2 *l2 = reinterpret_cast<const double2 *>(&Lt[k][cb]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        double2 l = l2[j];
+        s[2 * j] -= xk * l.x;
+        s[2 * j + 1] -= xk * l.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int jj = 0; jj < j; jj++) s[j] -= x[cb + jj] * Lt[cb + jj][cb + j];
+      x[cb + j] = s[j] * rdiag[cb + j];
+    }
   }
 #pragma unroll
   for (int c = 0; c < kNB; c++)
@@ -244,6 +282,47 @@ __global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *
 __global__ void gather_diag_kernel(const int64_t *__restrict__ diag_off, int n, const double *__restrict__ fac, double *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = fac[diag_off[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU barrier over peer-mapped flag words: every rank publishes `epoch` into its slot of every
+// peer's flag array, then waits until all peers have published theirs.  One kernel per GPU, each
+// GPU runs its own process's kernel, so the waits cannot starve each other.
+__global__ void peer_barrier(Peers peers, unsigned long long epoch) {
+  const int p = threadIdx.x;
+  __threadfence_system();
+  if (p < peers.n) {
+    unsigned long long *dst = peers.flags[p] + peers.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(dst), "l"(epoch) : "memory");
+    const unsigned long long *src = peers.flags[peers.rank] + p;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(src) : "memory");
+    } while (v < epoch);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+// Sum of all ranks' copies of the top panels: rank r reduces slice r (peer loads over NVLink, fixed
+// summation order, so every rank ends with bit-identical values) and stores the sums into every
+// copy (peer stores).  Bracketed by peer_barrier on both sides.
+__global__ void __launch_bounds__(256) allreduce_top(Peers peers, int64_t n2 /* double2 elements */) {
+  const int64_t lo = n2 * peers.rank / peers.n, hi = n2 * (peers.rank + 1) / peers.n;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; p++)
+      if (p < peers.n) v[p] = reinterpret_cast<const double2 *>(peers.fac[p])[i];
+    double2 s = v[0];
+#pragma unroll
+    for (int p = 1; p < kMaxPeers; p++)
+      if (p < peers.n) s.x += v[p].x, s.y += v[p].y;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; p++)
+      if (p < peers.n) reinterpret_cast<double2 *>(peers.fac[p])[i] = s;
+  }
+  __threadfence_system();
 }
 
 }  // namespace chb

@@ -3,15 +3,23 @@
 // Per tree level, leaves first (mmat.rg:1227), three phases that mirror the reference's three
 // __demand(__parallel) loops (mmat.rg:1240, 1259, 1293):
 //   (a) fused_dpotrf  -> blocked Cholesky of every pivot block of the level, in lock step:
-//                        left-looking over NBO-wide block columns (one grouped GEMM with K = all
-//                        columns to the left), right-looking over NB-wide tiles inside one
-//                        (tile POTRF, slab TRSM, small trailing GEMM).
+//                        NBO-wide block columns; inside one, NB-wide tiles (tile POTRF, slab TRSM,
+//                        small trailing GEMM); after one, a right-looking grouped GEMM (K = NBO) over
+//                        the whole trailing pivot block, which keeps the GPU full even for one front.
 //   (b) fused_dtrsm   -> the same blocking applied to the filled off-diagonal rows of the panels.
 //   (c) fused_dsyrk / fused_dgemm -> one grouped GEMM over DESTINATION clusters: every filled
 //                        cluster (g, p, ia, jb) owns the ordered list of its contributors
 //                        (s ascending), so accumulation is atomic-free and deterministic; the
 //                        extend-add index map is the precomputed destination offset.
+//
+// Multi-GPU (world = 2^d ranks, one process per GPU): rank r owns the subtree under heap index
+// 2^d + r and schedules only its separators on levels >= d.  Its Schur contributions to the top
+// d levels land in its own copy of the top panels; one K_ALLREDUCE sums the copies over NVLink.
+// On the top levels every rank runs the small kernels redundantly (bit-identical), while the large
+// grouped GEMMs are split by tiles across the ranks, each rank storing its tiles into every
+// rank's copy (shared launches), followed by a K_BARRIER.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "chol_internal.h"
@@ -26,14 +34,20 @@ struct Builder {
   Schedule &D;
   Builder(const Problem &p, const Symbolic &s, Schedule &d) : P(p), S(s), D(d) {}
 
-  // tiles of the launch being built, per tile configuration (0: 64x64, 1: 128x128)
-  std::vector<TileRef> cur[2];
-  double cur_flops[2] = {0, 0};
-  void begin_gemm() {
-    cur[0].clear(), cur[1].clear();
-    cur_flops[0] = cur_flops[1] = 0;
+  struct Pending {
+    int prob;
+    double flops;
+  };
+  std::vector<Pending> pend;
+  void begin_gemm() { pend.clear(); }
+  bool is_big(const GemmProblem &g) const { return g.M >= D.big_m && g.N >= D.big_n; }
+  static int64_t ntiles(const GemmProblem &g, int b) {
+    int64_t tr_n = (g.M + b - 1) / b, tc_n = (g.N + b - 1) / b;
+    if (!g.tri) return tr_n * tc_n;
+    int64_t t = 0;
+    for (int64_t tc = 0; tc < tc_n; tc++) t += std::max<int64_t>(0, tr_n - tc);
+    return t;
   }
-  int cfg_of(const GemmProblem &g) const { return (g.M >= D.big_m && g.N >= D.big_n) ? 1 : 0; }
   // one problem with a single contributor (in-panel updates)
   void add_problem(int64_t c_off, int ldc, int M, int N, int tri, int64_t a_off, int64_t b_off, int lda, int ldb, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return;
@@ -42,26 +56,46 @@ struct Builder {
     g.contrib_begin = (int)D.contribs.size(), g.contrib_count = 1;
     D.contribs.push_back(GemmContrib{a_off, b_off, lda, ldb, K, 0});
     D.probs.push_back(g);
-    add_tiles((int)D.probs.size() - 1, (tri ? 1.0 : 2.0) * M * N * K);
+    pend.push_back(Pending{(int)D.probs.size() - 1, (tri ? 1.0 : 2.0) * M * N * K});
   }
-  void add_tiles(int prob, double flops) {
-    const GemmProblem &g = D.probs[prob];
-    const int cfg = cfg_of(g), bm = cfg ? 128 : 64, bn = bm;
-    int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
-    for (int tc = 0; tc < tc_n; tc++)
-      for (int tr = 0; tr < tr_n; tr++) {
-        if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
-        cur[cfg].push_back(TileRef{prob, (uint16_t)tr, (uint16_t)tc});
-      }
-    cur_flops[cfg] += flops;
-  }
-  void end_gemm(int level, int phase) {
-    for (int cfg = 1; cfg >= 0; cfg--) {
-      if (cur[cfg].empty()) continue;
-      int64_t b = (int64_t)D.tiles.size();
-      D.tiles.insert(D.tiles.end(), cur[cfg].begin(), cur[cfg].end());
-      D.launches.push_back(Launch{K_GEMM, level, phase, b, (int64_t)cur[cfg].size(), cur_flops[cfg], cfg});
+  void emit(int level, int phase, int cfg, const std::vector<Pending> &list, bool top) {
+    if (list.empty()) return;
+    const int b = cfg ? 128 : 64;
+    int64_t begin = (int64_t)D.tiles.size();
+    double flops = 0;
+    for (const Pending &pd : list) {
+      const GemmProblem &g = D.probs[pd.prob];
+      int tr_n = (g.M + b - 1) / b, tc_n = (g.N + b - 1) / b;
+      for (int tc = 0; tc < tc_n; tc++)
+        for (int tr = 0; tr < tr_n; tr++) {
+          if (g.tri && (tr + 1) * b - 1 < tc * b) continue;  // wholly above the diagonal
+          D.tiles.push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+        }
+      flops += pd.flops;
     }
+    int64_t count = (int64_t)D.tiles.size() - begin;
+    int shared = 0;
+    if (top && D.world > 1 && flops >= D.shared_min_flops) {
+      // split the tile list across the ranks; every rank builds the same list, keeps its slice
+      int64_t lo = count * D.rank / D.world, hi = count * (D.rank + 1) / D.world;
+      flops *= (double)(hi - lo) / (double)std::max<int64_t>(1, count);
+      begin += lo, count = hi - lo;
+      shared = 1;
+    }
+    if (count > 0 || shared) D.launches.push_back(Launch{K_GEMM, level, phase, begin, count, flops, cfg, shared});
+    if (shared) D.launches.push_back(Launch{K_BARRIER, level, phase, 0, 0, 0, 0, 0});
+  }
+  // tile configuration is decided per launch: 128x128 tiles only pay when they fill the GPU
+  void end_gemm(int level, int phase, bool top) {
+    int64_t n128 = 0;
+    for (const Pending &pd : pend)
+      if (is_big(D.probs[pd.prob])) n128 += ntiles(D.probs[pd.prob], 128);
+    int64_t share = (top && D.world > 1) ? D.world : 1;
+    bool use128 = n128 >= (int64_t)D.min_tiles_128 * share;
+    std::vector<Pending> l128, l64;
+    for (const Pending &pd : pend) (use128 && is_big(D.probs[pd.prob]) ? l128 : l64).push_back(pd);
+    emit(level, phase, 1, l128, top);
+    emit(level, phase, 0, l64, top);
   }
 };
 
@@ -78,11 +112,23 @@ struct Pair {  // one (A cluster, B cluster) contribution of separator hs
 
 }  // namespace
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string &err) {
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, std::string &err) {
   D = Schedule();
+  D.rank = rank, D.world = world;
+  int depth = 0;
+  while ((1 << depth) < world) depth++;
+  if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
+  if (depth >= P.levels) return err = "more ranks than subtrees", -1;
+  D.depth = depth;
+  if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   const int L = P.levels, N = P.N;
   const int NB = D.nb, NBO = D.nbo, SLAB = D.slab;
   Builder B(P, S, D);
+  auto owner_of = [&](int h) -> int {  // -1: shared top separator
+    int lv = P.level_of(h);
+    return lv < depth ? -1 : (h >> (lv - depth)) - (1 << depth);
+  };
+  D.top_doubles = world > 1 ? S.poff[1 << depth] : 0;  // panels are laid out in heap order: the top ones come first
 
   // global permuted row of every segment start, per panel, for destination lookups
   std::vector<int> seg_grow(S.segs.size());
@@ -98,7 +144,8 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
     return s.off + local;
   };
 
-  // ---- assembly map (fill_block, mmat.rg:529-633, as a scatter)
+  // ---- assembly map (fill_block, mmat.rg:529-633, as a scatter).  With several ranks an entry is
+  // assembled by the owner of its column separator; top entries by rank 0 only (the copies are summed).
   {
     std::vector<int> iperm(P.n), rowheap(P.n);
     for (int p = 0; p < P.n; p++) iperm[P.perm[p]] = p;
@@ -112,6 +159,8 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
       int hr = rowheap[pi], hc = rowheap[pj];
       int d = P.level_of(hc) - P.level_of(hr);
       if (d < 0 || (hc >> d) != hr) continue;
+      int own = owner_of(hc);
+      if (world > 1 && !(own == rank || (own < 0 && rank == 0))) continue;
       int r = locate(hc, pi);
       if (r < 0) return err = "internal: nonzero outside the filled pattern", -1;
       D.a_off[e] = S.poff[hc] + r + (int64_t)(pj - P.start[hc]) * S.ld[hc];
@@ -120,7 +169,13 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
 
   std::vector<Pair> pairs;
   for (int lvl = L - 1; lvl >= 0; lvl--) {
-    const int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    const bool top = lvl < depth;
+    // separators of this level this rank works on
+    int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    if (!top && world > 1) {
+      h0 = ((1 << depth) + rank) << (lvl - depth);
+      h1 = h0 + (1 << (lvl - depth));
+    }
     int maxn = 0;
     for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
     const int nouter = (maxn + NBO - 1) / NBO;
@@ -130,22 +185,6 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
       const int phase = which == 0 ? PH_POTRF : PH_TRSM;
       for (int J = 0; J < nouter; J++) {
         const int c0 = J * NBO;
-        // left-looking update of block column J with everything to its left
-        if (J > 0) {
-          B.begin_gemm();
-          for (int h = h0; h < h1; h++) {
-            int n = P.sz[h], ld = S.ld[h];
-            if (n <= c0) continue;
-            int cw = std::min(NBO, n - c0);
-            int64_t base = S.poff[h];
-            if (which == 0) B.add_problem(base + c0 + (int64_t)c0 * ld, ld, n - c0, cw, 1, base + c0, base + c0, ld, ld, c0);
-            else {
-              int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
-              B.add_problem(base + r0 + (int64_t)c0 * ld, ld, m, cw, 0, base + r0, base + c0, ld, ld, c0);
-            }
-          }
-          B.end_gemm(lvl, phase);
-        }
         for (int jj = 0; jj < NBO / NB; jj++) {
           const int d0 = c0 + jj * NB;
           if (d0 >= maxn) break;
@@ -156,7 +195,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
               if (n <= d0) continue;
               D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
             }
-            if ((int64_t)D.potrf.size() > b) D.launches.push_back(Launch{K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0});
+            if ((int64_t)D.potrf.size() > b) D.launches.push_back(Launch{K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0, 0});
           }
           {
             int64_t b = (int64_t)D.trsm_tiles.size();
@@ -171,9 +210,9 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
               int ns = (rend - rbeg + SLAB - 1) / SLAB;
               for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
             }
-            if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0});
+            if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0, 0});
           }
-          // right-looking update of the rest of this outer block column
+          // right-looking update of the rest of this block column (K = NB)
           B.begin_gemm();
           for (int h = h0; h < h1; h++) {
             int n = P.sz[h], ld = S.ld[h];
@@ -188,8 +227,23 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
               B.add_problem(base + r0 + (int64_t)e0 * ld, ld, m, cend - e0, 0, base + r0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
             }
           }
-          B.end_gemm(lvl, phase);
+          B.end_gemm(lvl, phase, top);
         }
+        // right-looking update of everything to the right of block column J (K = NBO)
+        B.begin_gemm();
+        for (int h = h0; h < h1; h++) {
+          int n = P.sz[h], ld = S.ld[h];
+          int c1 = c0 + NBO;
+          if (n <= c1) continue;
+          int64_t base = S.poff[h];
+          if (which == 0)
+            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, n - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
+          else {
+            int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
+            B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
+          }
+        }
+        B.end_gemm(lvl, phase, top);
       }
     }
 
@@ -236,10 +290,13 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, std::string
         pf += (q.tri ? 1.0 : 2.0) * q.M * q.N * pairs[c].K;
       }
       D.probs.push_back(g);
-      B.add_tiles((int)D.probs.size() - 1, pf);
+      B.pend.push_back(Builder::Pending{(int)D.probs.size() - 1, pf});
       i = j;
     }
-    B.end_gemm(lvl, PH_UPDATE);
+    B.end_gemm(lvl, PH_UPDATE, top);
+
+    // the subtrees are done: sum every rank's copy of the top panels before the top is factored
+    if (world > 1 && lvl == depth) D.launches.push_back(Launch{K_ALLREDUCE, lvl, PH_UPDATE, 0, D.top_doubles, 0, 0, 0});
   }
   if (D.contribs.size() > 0x7fffffffULL || D.probs.size() > 0x7fffffffULL) return err = "schedule too large", -1;
   return 0;

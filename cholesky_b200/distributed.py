@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed only for the bootstrap.
+
+Rank r owns the subtree under heap index world + r; the log2(world) top levels are shared
+(SURVEY.md 8e).  The data path never goes through torch or NCCL: after the ranks have exchanged the
+CUDA-IPC handles of their factor buffers and flag words (one all_gather of 128 bytes per rank), the
+engine's own kernels sum the top-panel copies and broadcast the tiles of the shared launches through
+NVLink peer memory, and synchronise with a flag barrier in peer memory (csrc/kernels.cuh).
+"""
+import torch
+import torch.distributed as dist
+
+from .engine import Cholesky
+
+
+def make_partitioned(grid=None, files=None, keep_records=False):
+    """build this rank's engine: generate/load, set the partition, analyse"""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    ch = Cholesky(dev)
+    if grid is not None:
+        ch.generate(*grid)
+    else:
+        ch.load(*files)
+    ch.set_partition(rank, world)
+    ch.analyze(keep_records=keep_records)
+    return ch
+
+
+def exchange_peers(ch):
+    """all-gather the IPC handles and map every peer's buffers into this rank"""
+    world = dist.get_world_size()
+    if world == 1:
+        return
+    blob = ch.ipc_export()
+    backend = dist.get_backend()
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=device)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    ch.ipc_import([bytes(t.cpu().tolist()) for t in allb])
+    dist.barrier()
+
+
+def max_over_ranks(x):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x

@@ -152,6 +152,28 @@ class Cholesky:
         self._ck(self.L.chol_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
         return dict(potrf_ms=a.value, trsm_ms=b.value, gemm_ms=c.value, gemm_flops=f.value)
 
+    # ---- multi-GPU: one process and one handle per GPU (see cholesky_b200/distributed.py)
+    def set_partition(self, rank, world):
+        self._ck(self.L.chol_set_partition(self.h, rank, world))
+        return self
+
+    def ipc_export(self):
+        buf = (C.c_ubyte * 128)()
+        self._ck(self.L.chol_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def ipc_import(self, blobs):
+        world = len(blobs)
+        raw = b"".join(blobs)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.L.chol_ipc_import(self.h, buf, world))
+
+    def partition_stats(self):
+        out = np.zeros(6, dtype=np.float64)
+        self._ck(self.L.chol_partition_stats(self.h, _p(out)))
+        return dict(assembled=int(out[0]), gemm_flops=float(out[1]), shared_launches=int(out[2]),
+                    top_doubles=int(out[3]), potrf_tiles=int(out[4]), trsm_slabs=int(out[5]))
+
     def launches(self):
         """the compiled launch list as dicts (kind, level, phase, ctas, flops, cfg)"""
         out = []
@@ -160,8 +182,9 @@ class Cholesky:
         for i in range(int(self.L.chol_num_launches(self.h))):
             self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
                                    C.byref(ctas), C.byref(flops), C.byref(cfg))
-            out.append(dict(kind=("potrf_tile", "trsm_tile", "gemm_grouped")[kind.value], level=level.value,
-                            phase=phase.value, ctas=ctas.value, flops=flops.value, cfg=cfg.value))
+            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_barrier", "allreduce_top")
+            out.append(dict(kind=names[kind.value], level=level.value, phase=phase.value, ctas=ctas.value,
+                            flops=flops.value, cfg=cfg.value & 15, shared=cfg.value >> 4))
         return out
 
     # ---- results (mmat.rg:1360-1362)

@@ -103,6 +103,21 @@ int chol_get_launch(chol_t *, int64_t i, int *kind, int *level, int *phase, int6
 /* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
 int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops);
 
+/* ---- multi-GPU (one process and one handle per GPU; world = 1, 2, 4 or 8).  Rank r owns the subtree
+ * under heap index world + r; the top log2(world) levels are shared.  Call chol_set_partition before
+ * chol_analyze, then exchange the 128-byte IPC blobs of all ranks (any host-side all-gather) and hand
+ * the concatenation to chol_ipc_import; the factorization then exchanges data through NVLink peer
+ * memory from inside its own kernels.  Result accessors report the panels the rank owns (rank 0 also
+ * the shared top). */
+int chol_set_partition(chol_t *, int rank, int world);
+int chol_ipc_export(chol_t *, void *handles128);
+int chol_ipc_import(chol_t *, const void *all_handles, int world);
+/* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
+ * [2] tile-split (shared) launches, [3] doubles of the shared top region, [4] potrf tiles, [5] trsm slabs */
+int chol_partition_stats(chol_t *, double *out6);
+int chol_rank(chol_t *);
+int chol_world(chol_t *);
+
 /* ---- results.  replaces: write_matrix (mmat.rg:102-147) */
 int64_t chol_factor_nnz(chol_t *);                                           /* entries != 0 */
 int64_t chol_get_factor_coo(chol_t *, int32_t *I, int32_t *J, double *V);   /* 0-based permuted */
