@@ -126,7 +126,10 @@ struct Schedule {
   std::vector<int64_t> a_off;
   int nb = 64, nbo = 256, slab = 128;
   int big_m = 192, big_n = 128;  // problems at least this large may use the 128x128 tile configuration ...
-  int min_tiles_128 = 296;       // ... when the launch then still has two waves of CTAs (2 x 148 SMs)
+  // ... when the launch has at least this many such tiles.  Measured on B200 (128^3): four resident
+  // 64x64 CTAs per SM (27.5 TFLOP/s) beat one 128x128 CTA per SM (20.8 with 8 warps, 22.8 with 16),
+  // so the large configuration is off by default (CHOL_MIN_TILES_128 re-enables it for experiments).
+  int min_tiles_128 = 1 << 30;
   // multi-GPU partition (world = 2^depth ranks)
   int rank = 0, world = 1, depth = 0;
   int64_t top_doubles = 0;         // leading part of the factor buffer that holds the shared top panels

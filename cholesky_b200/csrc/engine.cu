@@ -17,8 +17,6 @@
 
 using namespace chb;
 
-typedef GemmCfg<64, 64, 16, 32, 32, 3> Gemm64;
-typedef GemmCfg<128, 128, 16, 64, 32, 4> Gemm128;
 
 struct chol {
   std::string err;
@@ -52,6 +50,7 @@ struct chol {
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  int gemm128_variant = 0;  // CHOL_GEMM128: 0 = 8 warps of 64x32, 1 = 16 warps of 32x32, 2 = 16 warps, BK 8
   std::vector<void *> ipc_opened;
 };
 
@@ -77,6 +76,7 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   if (!out) return -1;
   chol_t *c = new chol();
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
+  if (const char *e = getenv("CHOL_GEMM128")) c->gemm128_variant = atoi(e);
   *out = c;
   return 0;
 }
@@ -251,10 +251,6 @@ static int ensure_device(chol_t *c) {
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
-  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
-  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
-  CK(cudaFuncSetAttribute(gemm_grouped<64, 64, 16, 32, 32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::kSmemBytes));
-  CK(cudaFuncSetAttribute(gemm_grouped<128, 128, 16, 64, 32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::kSmemBytes));
   CK(cudaMalloc((void **)&c->d_flags, kMaxPeers * sizeof(unsigned long long)));
   CK(cudaMemset(c->d_flags, 0, kMaxPeers * sizeof(unsigned long long)));
   c->peers.n = 1, c->peers.rank = 0;
@@ -278,6 +274,24 @@ static int do_assemble(chol_t *c) {
   return 0;
 }
 
+}  // extern "C"
+template <int BM, int BN, int BK, int WM, int WN, int ST>
+static void launch_gemm(chol_t *c, const Launch &l) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, ST>;
+  static bool attr[2] = {false, false};  // one device per process
+  if (!attr[l.shared ? 1 : 0]) {
+    if (l.shared) cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    else cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr[l.shared ? 1 : 0] = true;
+  }
+  if (l.shared)
+    gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+  else
+    gemm_grouped<BM, BN, BK, WM, WN, ST, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+}
+extern "C" {
 static void launch_barrier(chol_t *c) {
   c->epoch++;
   peer_barrier<<<1, 32, 0, c->stream>>>(c->peers, c->epoch);
@@ -293,21 +307,12 @@ static int run_launch(chol_t *c, const Launch &l) {
       break;
     case K_GEMM:
       if (l.count <= 0) break;
-      if (l.shared) {
-        if (l.cfg == 1)
-          gemm_grouped<128, 128, 16, 64, 32, 4, true><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
-              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-        else
-          gemm_grouped<64, 64, 16, 32, 32, 3, true><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
-              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-      } else {
-        if (l.cfg == 1)
-          gemm_grouped<128, 128, 16, 64, 32, 4, false><<<(unsigned)l.count, Gemm128::kThreads, Gemm128::kSmemBytes, c->stream>>>(
-              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-        else
-          gemm_grouped<64, 64, 16, 32, 32, 3, false><<<(unsigned)l.count, Gemm64::kThreads, Gemm64::kSmemBytes, c->stream>>>(
-              c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-      }
+      if (l.cfg == 1) {
+        if (c->gemm128_variant == 1) launch_gemm<128, 128, 16, 32, 32, 4>(c, l);
+        else if (c->gemm128_variant == 2) launch_gemm<128, 128, 8, 32, 32, 6>(c, l);
+        else launch_gemm<128, 128, 16, 64, 32, 4>(c, l);
+      } else
+        launch_gemm<64, 64, 16, 32, 32, 3>(c, l);
       break;
     case K_BARRIER:
       launch_barrier(c);

@@ -160,51 +160,61 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
-// One thread per row, the row in registers.  Column k: thread k finishes its diagonal entry and
-// publishes row k through shared memory; every thread below takes a dot product with it.
+// One thread per row, the tile in shared memory (row stride 65: conflict-free).  Left-looking by
+// column: all rows at or below the diagonal take their dot product with row k at once, thread k
+// turns its result into 1/sqrt, the others scale.  Compact loops on purpose: a fully unrolled
+// version is instruction-fetch bound.
 __global__ void __launch_bounds__(kNB) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac, int *__restrict__ info) {
-  __shared__ double rowk[2][kNB + 2];
+  __shared__ double T[kNB][kNB + 1];
   const PotrfDesc d = descs[blockIdx.x];
   double *__restrict__ A = fac + d.off;
   const int nb = d.nb, i = threadIdx.x;
-  double a[kNB];
+  for (int c0 = 0; c0 < nb; c0 += 8) {  // eight coalesced column loads in flight per thread
+    double v[8];
 #pragma unroll
-  for (int c = 0; c < kNB; c++) a[c] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
+    for (int u = 0; u < 8; u++) v[u] = (i < nb && c0 + u <= i) ? A[i + (size_t)(c0 + u) * d.ld] : 0.0;
 #pragma unroll
-  for (int k = 0; k < kNB; k++) {
-    if (k < nb) {
-      double *rb = rowk[k & 1];
-      if (i == k) {
-        double s0 = a[k], s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-        for (int j = 0; j + 3 < k; j += 4) s0 -= a[j] * a[j], s1 -= a[j + 1] * a[j + 1], s2 -= a[j + 2] * a[j + 2], s3 -= a[j + 3] * a[j + 3];
-#pragma unroll
-        for (int j = k & ~3; j < k; j++) s0 -= a[j] * a[j];
-        double v = (s0 + s1) + (s2 + s3);
-        if (!(v > 0.0)) {
-          atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-          v = 1.0;
-        }
-        v = sqrt(v);
-        a[k] = v;
-#pragma unroll
-        for (int j = 0; j < k; j++) rb[j] = a[j];
-        rb[k] = v;
-      }
-      __syncthreads();
-      if (i > k) {
-        double s0 = a[k], s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-        for (int j = 0; j + 3 < k; j += 4) s0 -= a[j] * rb[j], s1 -= a[j + 1] * rb[j + 1], s2 -= a[j + 2] * rb[j + 2], s3 -= a[j + 3] * rb[j + 3];
-#pragma unroll
-        for (int j = k & ~3; j < k; j++) s0 -= a[j] * rb[j];
-        a[k] = ((s0 + s1) + (s2 + s3)) / rb[k];
-      }
-    }
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < kNB) T[i][c0 + u] = v[u];
   }
+  __syncthreads();
+  __shared__ double rk;  // 1 / L[k][k]
+  for (int k = 0; k < nb; k++) {
+    // every row at or below the diagonal takes its dot product with row k at the same time
+    double sk = 0.0;
+    if (i >= k && i < nb) {
+      double s0 = T[i][k], s1 = 0, s2 = 0, s3 = 0;
+      int j = 0;
+      for (; j + 7 < k; j += 8) {
+        double a0 = T[i][j], a1 = T[i][j + 1], a2 = T[i][j + 2], a3 = T[i][j + 3];
+        double a4 = T[i][j + 4], a5 = T[i][j + 5], a6 = T[i][j + 6], a7 = T[i][j + 7];
+        double b0 = T[k][j], b1 = T[k][j + 1], b2 = T[k][j + 2], b3 = T[k][j + 3];
+        double b4 = T[k][j + 4], b5 = T[k][j + 5], b6 = T[k][j + 6], b7 = T[k][j + 7];
+        s0 -= a0 * b0, s1 -= a1 * b1, s2 -= a2 * b2, s3 -= a3 * b3;
+        s0 -= a4 * b4, s1 -= a5 * b5, s2 -= a6 * b6, s3 -= a7 * b7;
+      }
+      for (; j < k; j++) s0 -= T[i][j] * T[k][j];
+      sk = (s0 + s1) + (s2 + s3);
+    }
+    if (i == k) {
+      if (!(sk > 0.0)) {
+        atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+        sk = 1.0;
+      }
+      const double r = rsqrt(sk);
+      T[k][k] = sk * r;
+      rk = r;
+    }
+    __syncthreads();
+    if (i > k && i < nb) T[i][k] = sk * rk;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < nb; c0 += 8) {
 #pragma unroll
-  for (int c = 0; c < kNB; c++)
-    if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = a[c];
+    for (int u = 0; u < 8; u++)
+      if (i < nb && c0 + u <= i && c0 + u < nb) A[i + (size_t)(c0 + u) * d.ld] = T[i][c0 + u];
+  }
 }
 
 // 128-row slab per CTA, one row per thread in registers.  L^T is staged in shared memory so that

@@ -120,6 +120,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
   if (depth >= P.levels) return err = "more ranks than subtrees", -1;
   D.depth = depth;
+  if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);  // tuning knob
   if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   const int L = P.levels, N = P.N;
   const int NB = D.nb, NBO = D.nbo, SLAB = D.slab;
