@@ -110,7 +110,7 @@ struct Launch {
   int phase;
   int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
-  int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128
+  int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128, 2 = 128x64
   int shared;            // multi-GPU: this rank runs a slice of the tiles and stores into every rank's copy
 };
 
@@ -130,13 +130,15 @@ struct Schedule {
   // 64x64 CTAs per SM (27.5 TFLOP/s) beat one 128x128 CTA per SM (20.8 with 8 warps, 22.8 with 16),
   // so the large configuration is off by default (CHOL_MIN_TILES_128 re-enables it for experiments).
   int min_tiles_128 = 1 << 30;
+  int big_cfg = 1;  // tile configuration of big problems: 1 = 128x128, 2 = 128x64
   // multi-GPU partition (world = 2^depth ranks)
   int rank = 0, world = 1, depth = 0;
+  bool split_phases = false;  // true: fused_dpotrf and fused_dtrsm as separate launch sequences (piecewise API)
   int64_t top_doubles = 0;         // leading part of the factor buffer that holds the shared top panels
   double shared_min_flops = 2e9;   // top-level GEMM launches at least this large are split across ranks
 };
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, std::string &err);
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err);
 
 uint64_t mix64(uint64_t x);
 uint64_t filled_hash(const FilledRec &r);

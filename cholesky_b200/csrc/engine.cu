@@ -44,12 +44,15 @@ struct chol {
   bool h_fac_valid = false;
   double k_ms[5] = {0, 0, 0, 0, 0};
   double k_gemm_flops = 0;
+  std::vector<float> launch_ms;  // per launch, from the last instrumented pass
   // multi-GPU: one handle per rank; peers' factor buffers and flag words mapped through CUDA IPC
   int rank = 0, world = 1;
   Peers peers = {};
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
+                            // 128^3), 2 = same with 4 stages / 3 CTAs per SM, 0 = cp.async kernel
   int gemm128_variant = 0;  // CHOL_GEMM128: 0 = 8 warps of 64x32, 1 = 16 warps of 32x32, 2 = 16 warps, BK 8
   std::vector<void *> ipc_opened;
 };
@@ -77,6 +80,7 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   chol_t *c = new chol();
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
   if (const char *e = getenv("CHOL_GEMM128")) c->gemm128_variant = atoi(e);
+  if (const char *e = getenv("CHOL_GEMM_WS")) c->gemm_ws = atoi(e);
   *out = c;
   return 0;
 }
@@ -157,7 +161,7 @@ int chol_analyze(chol_t *c, int keep_records) {
   free_device(c);
   c->analyzed = false;
   if (analyze(c->P, c->S, keep_records != 0, c->err)) return -1;
-  if (build_schedule(c->P, c->S, c->D, c->rank, c->world, c->err)) return -1;
+  if (build_schedule(c->P, c->S, c->D, c->rank, c->world, false, c->err)) return -1;
   c->analyzed = true;
   c->assembled = false;
   c->h_fac_valid = false;
@@ -227,6 +231,26 @@ static int upload(chol_t *c, T **dst, const std::vector<T> &src) {
 }
 
 extern "C" {
+static int upload_schedule(chol_t *c) {
+  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles);
+  c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_potrf = nullptr, c->d_trsm = nullptr, c->d_trsm_tiles = nullptr;
+  if (upload(c, &c->d_probs, c->D.probs)) return -100;
+  if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
+  if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
+  if (upload(c, &c->d_potrf, c->D.potrf)) return -100;
+  if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
+  if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
+  return 0;
+}
+// chol_factor runs the fused schedule (pivot block and off-diagonal rows advance together); the
+// piecewise fused_dpotrf / fused_dtrsm entry points need the two phases as separate launch sequences
+static int ensure_schedule(chol_t *c, bool split) {
+  if (c->D.split_phases == split) return 0;
+  CK(cudaStreamSynchronize(c->stream));
+  if (build_schedule(c->P, c->S, c->D, c->rank, c->world, split, c->err)) return -1;
+  return upload_schedule(c);
+}
+
 static int ensure_device(chol_t *c) {
   if (!c->analyzed) return fail(c, "analyze first");
   if (c->device_ready) return 0;
@@ -239,12 +263,7 @@ static int ensure_device(chol_t *c) {
   c->device_ready = true;
   if (upload(c, &c->d_vals, c->P.ev)) return -100;
   if (upload(c, &c->d_aoff, c->D.a_off)) return -100;
-  if (upload(c, &c->d_probs, c->D.probs)) return -100;
-  if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
-  if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
-  if (upload(c, &c->d_potrf, c->D.potrf)) return -100;
-  if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
-  if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
+  if (upload_schedule(c)) return -100;
   CK(cudaMalloc((void **)&c->d_info, sizeof(int)));
   std::vector<int64_t> doff(c->P.n);
   for (int h = 1; h <= c->P.N; h++)
@@ -291,6 +310,22 @@ static void launch_gemm(chol_t *c, const Launch &l) {
     gemm_grouped<BM, BN, BK, WM, WN, ST, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
 }
+template <int BM, int BN, int BK, int WM, int WN, int ST, int MINB>
+static void launch_gemm_ws(chol_t *c, const Launch &l) {
+  using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, ST>;
+  static bool attr[2] = {false, false};
+  if (!attr[l.shared ? 1 : 0]) {
+    if (l.shared) cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    else cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr[l.shared ? 1 : 0] = true;
+  }
+  if (l.shared)
+    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+  else
+    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
+}
 extern "C" {
 static void launch_barrier(chol_t *c) {
   c->epoch++;
@@ -307,11 +342,19 @@ static int run_launch(chol_t *c, const Launch &l) {
       break;
     case K_GEMM:
       if (l.count <= 0) break;
-      if (l.cfg == 1) {
+      if (l.cfg == 2)
+        launch_gemm_ws<128, 64, 16, 32, 32, 4, 2>(c, l);
+      else if (l.cfg == 1 && c->gemm_ws)
+        launch_gemm_ws<128, 128, 16, 32, 32, 4, 1>(c, l);
+      else if (l.cfg == 1) {
         if (c->gemm128_variant == 1) launch_gemm<128, 128, 16, 32, 32, 4>(c, l);
         else if (c->gemm128_variant == 2) launch_gemm<128, 128, 8, 32, 32, 6>(c, l);
         else launch_gemm<128, 128, 16, 64, 32, 4>(c, l);
-      } else
+      } else if (c->gemm_ws == 1)
+        launch_gemm_ws<64, 64, 16, 32, 32, 3, 4>(c, l);
+      else if (c->gemm_ws == 2)
+        launch_gemm_ws<64, 64, 16, 32, 32, 4, 3>(c, l);
+      else
         launch_gemm<64, 64, 16, 32, 32, 3>(c, l);
       break;
     case K_BARRIER:
@@ -348,10 +391,12 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
     CK(cudaStreamSynchronize(c->stream));
     for (double &m : c->k_ms) m = 0;
     c->k_gemm_flops = 0;
+    c->launch_ms.assign(kinds.size(), 0.f);
     for (size_t i = 0; i < kinds.size(); i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
       c->k_ms[kinds[i]] += ms;
+      c->launch_ms[i] = ms;
       if (kinds[i] == K_GEMM) c->k_gemm_flops += fl[i];
       cudaEventDestroy(ev[2 * i]), cudaEventDestroy(ev[2 * i + 1]);
     }
@@ -376,6 +421,7 @@ static int fetch_info(chol_t *c, int *info) {
 
 int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
   if (ensure_device(c)) return -1;
+  if (ensure_schedule(c, false)) return -1;
   if (iterations < 1) iterations = 1;
   std::vector<double> secs;
   double asm_s = 0;
@@ -417,6 +463,7 @@ static int piecewise(chol_t *c, int lvl, int phase) {
   if (ensure_device(c)) return -1;
   if (!c->assembled) return fail(c, "assemble first");
   if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
+  if (ensure_schedule(c, phase != PH_UPDATE || c->D.split_phases)) return -1;
   c->h_fac_valid = false;
   if (run_levels(c, lvl, lvl, phase, false)) return -1;
   CK(cudaStreamSynchronize(c->stream));
@@ -428,6 +475,7 @@ int chol_fused_update(chol_t *c, int lvl) { return piecewise(c, lvl, PH_UPDATE);
 
 int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_out, chol_stats_t *st) {
   if (ensure_device(c)) return -1;
+  if (ensure_schedule(c, false)) return -1;
   if (values && nz != c->P.nz) return fail(c, "value count differs from the loaded pattern");
   size_t need = std::max((size_t)c->P.nz, (size_t)c->P.n) * sizeof(double);
   if (c->h_pinned_bytes < need) {
@@ -517,6 +565,12 @@ int chol_partition_stats(chol_t *c, double *out6) {
 int chol_rank(chol_t *c) { return c->rank; }
 int chol_world(chol_t *c) { return c->world; }
 
+/* per-launch device time (ms) of the last chol_kernel_times pass, in launch-list order */
+int64_t chol_launch_times(chol_t *c, float *ms, int64_t cap) {
+  int64_t n = std::min<int64_t>(cap, (int64_t)c->launch_ms.size());
+  for (int64_t i = 0; i < n; i++) ms[i] = c->launch_ms[i];
+  return (int64_t)c->launch_ms.size();
+}
 int64_t chol_num_launches(chol_t *c) { return c->analyzed ? (int64_t)c->D.launches.size() : -1; }
 int chol_get_launch(chol_t *c, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg) {
   if (!c->analyzed || i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
@@ -533,6 +587,7 @@ int chol_synchronize(chol_t *c) {
 
 int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops) {
   if (ensure_device(c)) return -1;
+  if (ensure_schedule(c, false)) return -1;
   if (do_assemble(c)) return -1;
   if (run_levels(c, c->P.levels - 1, 0, 7, true)) return -1;
   if (potrf_ms) *potrf_ms = c->k_ms[K_POTRF];

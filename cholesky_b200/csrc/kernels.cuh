@@ -158,6 +158,193 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// gemm_grouped_ws: the same grouped update, warp-specialised.  One producer warp stages operand
+// tiles with the TMA bulk-copy engine (cp.async.bulk global -> shared, SASS UBLKCP; every column of
+// a column-major tile is one contiguous 16-byte aligned run, so no tensor map is needed) and signals
+// the consumers through mbarriers (expect_tx / complete_tx); WM x WN consumer warps issue FP64 DMMA
+// and hand stages back through a second set of mbarriers.  No block-wide barrier in the main loop,
+// the stage ring keeps running across the contributors of a destination tile (K-concatenation).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+struct GemmWsCfg {
+  static constexpr int kWarpsM = BM / WM, kWarpsN = BN / WN;
+  static constexpr int kConsumers = kWarpsM * kWarpsN;
+  static constexpr int kThreads = (kConsumers + 1) * 32;
+  static constexpr int kPad = 4;
+  static constexpr int kLdA = BM + kPad, kLdB = BN + kPad;
+  static constexpr int kStageDoubles = BK * (kLdA + kLdB);
+  static constexpr int kSmemBytes = STAGES * kStageDoubles * 8 + 2 * STAGES * 8 + STAGES * 4 + 64;
+};
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool SHARED>
+__global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThreads, MINB)
+    gemm_grouped_ws(const GemmProblem *__restrict__ probs, const GemmContrib *__restrict__ contribs,
+                    const TileRef *__restrict__ tiles, double *__restrict__ fac, Peers peers) {
+  using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, STAGES>;
+  static_assert(BK * 2 <= 32 || BK == 32, "one bulk copy per producer lane");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *smem = reinterpret_cast<double *>(smem_raw);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + STAGES * Cfg::kStageDoubles * 8);
+  unsigned long long *empty = full + STAGES;
+  int *kvalid = reinterpret_cast<int *>(empty + STAGES);
+
+  const TileRef tile = tiles[blockIdx.x];
+  const GemmProblem pr = probs[tile.prob];
+  const int row0 = tile.tr * BM, col0 = tile.tc * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mrem = pr.M - row0, nrem = pr.N - col0;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], Cfg::kConsumers);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == Cfg::kConsumers) {
+    // ===== producer warp: lane l < BK copies column l of the A tile, lane BK + l column l of the B tile
+    const unsigned a_bytes = (unsigned)(min(BM, (mrem + 1) & ~1) * 8), b_bytes = (unsigned)(min(BN, (nrem + 1) & ~1) * 8);
+    int it = 0;
+    for (int c = 0; c < pr.contrib_count; c++) {
+      const GemmContrib cb = contribs[pr.contrib_begin + c];
+      const double *__restrict__ A = fac + cb.a_off + row0;
+      const double *__restrict__ Bp = fac + cb.b_off + col0;
+      for (int k0 = 0; k0 < cb.K; k0 += BK, it++) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+        const int kv = min(BK, cb.K - k0);
+        double *As = smem + s * Cfg::kStageDoubles;
+        double *Bs = As + BK * Cfg::kLdA;
+        if (lane == 0) {
+          kvalid[s] = kv;
+          mbar_arrive_expect_tx(&full[s], (unsigned)kv * (a_bytes + b_bytes));
+        }
+        __syncwarp();
+        if (BK <= 16) {
+          const int kk = lane & (BK - 1);
+          if (kk < kv) {
+            if (lane < BK) bulk_g2s(As + kk * Cfg::kLdA, A + (size_t)(k0 + kk) * cb.lda, a_bytes, &full[s]);
+            else if (lane < 2 * BK) bulk_g2s(Bs + kk * Cfg::kLdB, Bp + (size_t)(k0 + kk) * cb.ldb, b_bytes, &full[s]);
+          }
+        } else {
+          if (lane < kv) {
+            bulk_g2s(As + lane * Cfg::kLdA, A + (size_t)(k0 + lane) * cb.lda, a_bytes, &full[s]);
+            bulk_g2s(Bs + lane * Cfg::kLdB, Bp + (size_t)(k0 + lane) * cb.ldb, b_bytes, &full[s]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % Cfg::kWarpsM) * WM, wn0 = (warp / Cfg::kWarpsM) * WN;
+  constexpr int MB = WM / 8, NBk = WN / 8;
+  double acc[MB][NBk][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NBk; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  int total = 0;
+  for (int c = 0; c < pr.contrib_count; c++) total += (contribs[pr.contrib_begin + c].K + BK - 1) / BK;
+  for (int it = 0; it < total; it++) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const int kv = kvalid[s];
+    const double *As = smem + s * Cfg::kStageDoubles;
+    const double *Bs = As + BK * Cfg::kLdA;
+    if (kv == BK) {
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; k4++) {
+        double a[MB], b[NBk];
+#pragma unroll
+        for (int i = 0; i < MB; i++) a[i] = As[(k4 * 4 + t) * Cfg::kLdA + wm0 + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < NBk; j++) b[j] = Bs[(k4 * 4 + t) * Cfg::kLdB + wn0 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < MB; i++)
+#pragma unroll
+          for (int j = 0; j < NBk; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {  // K tail of a contributor: columns >= kv of the stage are stale, feed zeros instead
+      for (int k4 = 0; k4 * 4 < kv; k4++) {
+        const bool ok = k4 * 4 + t < kv;
+        double a[MB], b[NBk];
+#pragma unroll
+        for (int i = 0; i < MB; i++) a[i] = ok ? As[(k4 * 4 + t) * Cfg::kLdA + wm0 + i * 8 + g] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NBk; j++) b[j] = ok ? Bs[(k4 * 4 + t) * Cfg::kLdB + wn0 + j * 8 + g] : 0.0;
+#pragma unroll
+        for (int i = 0; i < MB; i++)
+#pragma unroll
+          for (int j = 0; j < NBk; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  double *__restrict__ C = fac + pr.c_off;
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int r = row0 + wm0 + i * 8 + g;
+    if (r >= pr.M) continue;
+#pragma unroll
+    for (int j = 0; j < NBk; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+        if (cc < pr.N && (!pr.tri || r >= cc)) {
+          const size_t o = r + (size_t)cc * pr.ldc;
+          const double v = C[o] - acc[i][j][e];
+          if (SHARED) {
+#pragma unroll
+            for (int p = 0; p < kMaxPeers; p++)
+              if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
+          } else
+            C[o] = v;
+        }
+      }
+    }
+  }
+  if (SHARED) __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
 // One thread per row, the tile in shared memory (row stride 65: conflict-free).  Left-looking by

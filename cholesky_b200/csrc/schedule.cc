@@ -41,11 +41,15 @@ struct Builder {
   std::vector<Pending> pend;
   void begin_gemm() { pend.clear(); }
   bool is_big(const GemmProblem &g) const { return g.M >= D.big_m && g.N >= D.big_n; }
-  static int64_t ntiles(const GemmProblem &g, int b) {
-    int64_t tr_n = (g.M + b - 1) / b, tc_n = (g.N + b - 1) / b;
+  static int cfg_bm(int cfg) { return cfg == 0 ? 64 : 128; }
+  static int cfg_bn(int cfg) { return cfg == 1 ? 128 : 64; }
+  static int64_t ntiles(const GemmProblem &g, int cfg) {
+    const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
+    int64_t tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
     if (!g.tri) return tr_n * tc_n;
     int64_t t = 0;
-    for (int64_t tc = 0; tc < tc_n; tc++) t += std::max<int64_t>(0, tr_n - tc);
+    for (int64_t tc = 0; tc < tc_n; tc++)
+      for (int64_t tr = 0; tr < tr_n; tr++) t += !((tr + 1) * bm - 1 < tc * bn);
     return t;
   }
   // one problem with a single contributor (in-panel updates)
@@ -56,19 +60,20 @@ struct Builder {
     g.contrib_begin = (int)D.contribs.size(), g.contrib_count = 1;
     D.contribs.push_back(GemmContrib{a_off, b_off, lda, ldb, K, 0});
     D.probs.push_back(g);
-    pend.push_back(Pending{(int)D.probs.size() - 1, (tri ? 1.0 : 2.0) * M * N * K});
+    // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
+    pend.push_back(Pending{(int)D.probs.size() - 1, 2.0 * K * ((double)M * N - (tri ? 0.5 * N * (N - 1.0) : 0.0))});
   }
   void emit(int level, int phase, int cfg, const std::vector<Pending> &list, bool top) {
     if (list.empty()) return;
-    const int b = cfg ? 128 : 64;
+    const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
     int64_t begin = (int64_t)D.tiles.size();
     double flops = 0;
     for (const Pending &pd : list) {
       const GemmProblem &g = D.probs[pd.prob];
-      int tr_n = (g.M + b - 1) / b, tc_n = (g.N + b - 1) / b;
+      int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
       for (int tc = 0; tc < tc_n; tc++)
         for (int tr = 0; tr < tr_n; tr++) {
-          if (g.tri && (tr + 1) * b - 1 < tc * b) continue;  // wholly above the diagonal
+          if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
           D.tiles.push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
         }
       flops += pd.flops;
@@ -89,12 +94,12 @@ struct Builder {
   void end_gemm(int level, int phase, bool top) {
     int64_t n128 = 0;
     for (const Pending &pd : pend)
-      if (is_big(D.probs[pd.prob])) n128 += ntiles(D.probs[pd.prob], 128);
+      if (is_big(D.probs[pd.prob])) n128 += ntiles(D.probs[pd.prob], D.big_cfg);
     int64_t share = (top && D.world > 1) ? D.world : 1;
     bool use128 = n128 >= (int64_t)D.min_tiles_128 * share;
     std::vector<Pending> l128, l64;
     for (const Pending &pd : pend) (use128 && is_big(D.probs[pd.prob]) ? l128 : l64).push_back(pd);
-    emit(level, phase, 1, l128, top);
+    emit(level, phase, D.big_cfg, l128, top);
     emit(level, phase, 0, l64, top);
   }
 };
@@ -112,14 +117,16 @@ struct Pair {  // one (A cluster, B cluster) contribution of separator hs
 
 }  // namespace
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, std::string &err) {
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err) {
   D = Schedule();
   D.rank = rank, D.world = world;
+  D.split_phases = split_phases;
   int depth = 0;
   while ((1 << depth) < world) depth++;
   if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
   if (depth >= P.levels) return err = "more ranks than subtrees", -1;
   D.depth = depth;
+  if (const char *e = getenv("CHOL_BIG_CFG")) D.big_cfg = atoi(e);  // tuning knob: 1 = 128x128, 2 = 128x64
   if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);  // tuning knob
   if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   const int L = P.levels, N = P.N;
@@ -181,15 +188,17 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
     const int nouter = (maxn + NBO - 1) / NBO;
 
-    // which == 0: pivot blocks (rows [0, n));  which == 1: off-diagonal rows [r0, R)
-    for (int which = 0; which < 2; which++) {
-      const int phase = which == 0 ? PH_POTRF : PH_TRSM;
+    // which == 0: pivot blocks (rows [0, n));  which == 1: off-diagonal rows [r0, R);  which == 2: both at
+    // once (rows [0, R)): the default, it halves the number of dependent small launches.  The split form
+    // serves the piecewise fused_dpotrf / fused_dtrsm entry points.
+    for (int which = (D.split_phases ? 0 : 2); which < (D.split_phases ? 2 : 3); which++) {
+      const int phase = which == 0 ? PH_POTRF : which == 1 ? PH_TRSM : (PH_POTRF | PH_TRSM);
       for (int J = 0; J < nouter; J++) {
         const int c0 = J * NBO;
         for (int jj = 0; jj < NBO / NB; jj++) {
           const int d0 = c0 + jj * NB;
           if (d0 >= maxn) break;
-          if (which == 0) {
+          if (which != 1) {
             int64_t b = (int64_t)D.potrf.size();
             for (int h = h0; h < h1; h++) {
               int n = P.sz[h];
@@ -204,7 +213,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
               int n = P.sz[h], ld = S.ld[h];
               if (n <= d0) continue;
               int dw = std::min(NB, n - d0);
-              int rbeg = which == 0 ? d0 + dw : (n + 1) / 2 * 2;
+              int rbeg = which == 1 ? (n + 1) / 2 * 2 : d0 + dw;
               int rend = which == 0 ? n : S.rows[h];
               if (rend <= rbeg) continue;
               D.trsm.push_back(TrsmDesc{S.poff[h] + d0 + (int64_t)d0 * ld, S.poff[h] + rbeg + (int64_t)d0 * ld, ld, dw, rend - rbeg, 0});
@@ -221,8 +230,9 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
             int dw = std::min(NB, n - d0), e0 = d0 + dw, cend = std::min(c0 + NBO, n);
             if (e0 >= cend) continue;
             int64_t base = S.poff[h];
-            if (which == 0)
-              B.add_problem(base + e0 + (int64_t)e0 * ld, ld, n - e0, cend - e0, 1, base + e0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+            if (which != 1)
+              B.add_problem(base + e0 + (int64_t)e0 * ld, ld, (which == 0 ? n : S.rows[h]) - e0, cend - e0, 1, base + e0 + (int64_t)d0 * ld,
+                            base + e0 + (int64_t)d0 * ld, ld, ld, dw);
             else {
               int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
               B.add_problem(base + r0 + (int64_t)e0 * ld, ld, m, cend - e0, 0, base + r0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
@@ -237,8 +247,9 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           int c1 = c0 + NBO;
           if (n <= c1) continue;
           int64_t base = S.poff[h];
-          if (which == 0)
-            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, n - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
+          if (which != 1)
+            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, (which == 0 ? n : S.rows[h]) - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld,
+                          base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
           else {
             int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
             B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
@@ -288,7 +299,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
       for (size_t c = i; c < j; c++) {
         if (pairs[c].M != q.M || pairs[c].N != q.N || pairs[c].tri != q.tri) return err = "internal: contributors of one destination cluster disagree on its shape", -1;
         D.contribs.push_back(GemmContrib{pairs[c].a_off, pairs[c].b_off, pairs[c].ld, pairs[c].ld, pairs[c].K, 0});
-        pf += (q.tri ? 1.0 : 2.0) * q.M * q.N * pairs[c].K;
+        pf += 2.0 * pairs[c].K * ((double)q.M * q.N - (q.tri ? 0.5 * q.N * (q.N - 1.0) : 0.0));
       }
       D.probs.push_back(g);
       B.pend.push_back(Builder::Pending{(int)D.probs.size() - 1, pf});

@@ -174,6 +174,13 @@ class Cholesky:
         return dict(assembled=int(out[0]), gemm_flops=float(out[1]), shared_launches=int(out[2]),
                     top_doubles=int(out[3]), potrf_tiles=int(out[4]), trsm_slabs=int(out[5]))
 
+    def launch_times(self):
+        """per-launch device ms of the last kernel_times() pass (launch-list order)"""
+        n = int(self.L.chol_num_launches(self.h))
+        out = np.zeros(n, dtype=np.float32)
+        self.L.chol_launch_times(self.h, _p(out), C.c_int64(n))
+        return out
+
     def launches(self):
         """the compiled launch list as dicts (kind, level, phase, ctas, flops, cfg)"""
         out = []

@@ -102,6 +102,8 @@ int64_t chol_num_launches(chol_t *);
 int chol_get_launch(chol_t *, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg);
 /* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
 int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops);
+/* per-launch device time (ms) of that instrumented pass, in launch-list order; returns the count */
+int64_t chol_launch_times(chol_t *, float *ms, int64_t cap);
 
 /* ---- multi-GPU (one process and one handle per GPU; world = 1, 2, 4 or 8).  Rank r owns the subtree
  * under heap index world + r; the top log2(world) levels are shared.  Call chol_set_partition before

@@ -20,7 +20,7 @@ def _ngpu():
 def test_partitioned_factor_matches_oracle(world, grid):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, CHOL_SHARED_MIN_FLOPS="1e5")
+    env = dict(os.environ, CHOL_SHARED_MIN_FLOPS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), grid]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
