@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from bench import WORKLOADS  # noqa: E402
 from cholesky_b200 import Cholesky  # noqa: E402
 
-PHASE = {1: "fused_dpotrf", 2: "fused_dtrsm", 4: "fused_dsyrk/dgemm"}
+PHASE = {1: "fused_dpotrf", 2: "fused_dtrsm", 3: "fused_dpotrf+dtrsm", 4: "fused_dsyrk/dgemm"}
 
 
 def main():
