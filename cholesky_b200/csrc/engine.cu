@@ -298,12 +298,12 @@ template <int BM, int BN, int BK, int WM, int WN, int ST>
 static void launch_gemm(chol_t *c, const Launch &l) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, ST>;
   static bool attr[2] = {false, false};  // one device per process
-  if (!attr[l.shared ? 1 : 0]) {
-    if (l.shared) cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (!attr[(l.shared == 1) ? 1 : 0]) {
+    if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     else cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    attr[l.shared ? 1 : 0] = true;
+    attr[(l.shared == 1) ? 1 : 0] = true;
   }
-  if (l.shared)
+  if (l.shared == 1)
     gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
   else
@@ -314,12 +314,12 @@ template <int BM, int BN, int BK, int WM, int WN, int ST, int MINB>
 static void launch_gemm_ws(chol_t *c, const Launch &l) {
   using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, ST>;
   static bool attr[2] = {false, false};
-  if (!attr[l.shared ? 1 : 0]) {
-    if (l.shared) cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (!attr[(l.shared == 1) ? 1 : 0]) {
+    if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     else cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    attr[l.shared ? 1 : 0] = true;
+    attr[(l.shared == 1) ? 1 : 0] = true;
   }
-  if (l.shared)
+  if (l.shared == 1)
     gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
   else
@@ -555,7 +555,7 @@ int chol_partition_stats(chol_t *c, double *out6) {
   double a = 0, f = 0, sh = 0, pt = 0, ts = 0;
   for (int64_t o : c->D.a_off) a += (o >= 0);
   for (const Launch &l : c->D.launches) {
-    if (l.kind == K_GEMM) f += l.flops, sh += l.shared;
+    if (l.kind == K_GEMM) f += l.flops, sh += (l.shared == 1);
     if (l.kind == K_POTRF) pt += (double)l.count;
     if (l.kind == K_TRSM) ts += (double)l.count;
   }

@@ -37,9 +37,17 @@ struct Builder {
   struct Pending {
     int prob;
     double flops;
+    // in-panel right-looking update of a shared top panel: tile rows are owned by rank
+    // (row_tile0 + tr) % world for the whole panel factorization, so a tile is only stored locally
+    // until it belongs to the next block column (tile columns < bcast_tc), which every rank needs
+    int row_tile0 = -1, bcast_tc = 0;
   };
   std::vector<Pending> pend;
-  void begin_gemm() { pend.clear(); }
+  int mode = 0;  // 0: ordinary launch; 1: in-panel block-column update (owned tiles); 2: never split
+  void begin_gemm(int m = 0) {
+    pend.clear();
+    mode = m;
+  }
   bool is_big(const GemmProblem &g) const { return g.M >= D.big_m && g.N >= D.big_n; }
   static int cfg_bm(int cfg) { return cfg == 0 ? 64 : 128; }
   static int cfg_bn(int cfg) { return cfg == 1 ? 128 : 64; }
@@ -53,7 +61,8 @@ struct Builder {
     return t;
   }
   // one problem with a single contributor (in-panel updates)
-  void add_problem(int64_t c_off, int ldc, int M, int N, int tri, int64_t a_off, int64_t b_off, int lda, int ldb, int K) {
+  void add_problem(int64_t c_off, int ldc, int M, int N, int tri, int64_t a_off, int64_t b_off, int lda, int ldb, int K,
+                   int row_tile0 = -1, int bcast_tc = 0) {
     if (M <= 0 || N <= 0 || K <= 0) return;
     GemmProblem g;
     g.c_off = c_off, g.ldc = ldc, g.M = M, g.N = N, g.tri = tri;
@@ -61,11 +70,45 @@ struct Builder {
     D.contribs.push_back(GemmContrib{a_off, b_off, lda, ldb, K, 0});
     D.probs.push_back(g);
     // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
-    pend.push_back(Pending{(int)D.probs.size() - 1, 2.0 * K * ((double)M * N - (tri ? 0.5 * N * (N - 1.0) : 0.0))});
+    Pending pd;
+    pd.prob = (int)D.probs.size() - 1;
+    pd.flops = 2.0 * K * ((double)M * N - (tri ? 0.5 * N * (N - 1.0) : 0.0));
+    pd.row_tile0 = row_tile0, pd.bcast_tc = bcast_tc;
+    pend.push_back(pd);
+  }
+  void push_launch(int level, int phase, int cfg, int64_t begin, int64_t count, double flops, int shared) {
+    if (count > 0 || shared == 1) D.launches.push_back(Launch{K_GEMM, level, phase, begin, count, flops, cfg, shared});
+    if (shared == 1) D.launches.push_back(Launch{K_BARRIER, level, phase, 0, 0, 0, 0, 0});
   }
   void emit(int level, int phase, int cfg, const std::vector<Pending> &list, bool top) {
     if (list.empty()) return;
     const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
+    const bool multi = top && D.world > 1;
+    if (multi && mode == 1 && cfg == 0) {
+      // owned tiles: the next block column's tiles are stored into every rank's copy, the rest locally
+      double all_tiles = 0, flops = 0;
+      std::vector<TileRef> bc, loc;
+      for (const Pending &pd : list) {
+        const GemmProblem &g = D.probs[pd.prob];
+        int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
+        for (int tc = 0; tc < tc_n; tc++)
+          for (int tr = 0; tr < tr_n; tr++) {
+            if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;
+            all_tiles += 1;
+            if ((pd.row_tile0 + tr) % D.world != D.rank) continue;
+            (tc < pd.bcast_tc ? bc : loc).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+          }
+        flops += pd.flops;
+      }
+      const double per_tile = flops / std::max(1.0, all_tiles);
+      int64_t b0 = (int64_t)D.tiles.size();
+      D.tiles.insert(D.tiles.end(), bc.begin(), bc.end());
+      push_launch(level, phase, cfg, b0, (int64_t)bc.size(), per_tile * (double)bc.size(), 1);
+      int64_t b1 = (int64_t)D.tiles.size();
+      D.tiles.insert(D.tiles.end(), loc.begin(), loc.end());
+      push_launch(level, phase, cfg, b1, (int64_t)loc.size(), per_tile * (double)loc.size(), 2);
+      return;
+    }
     int64_t begin = (int64_t)D.tiles.size();
     double flops = 0;
     for (const Pending &pd : list) {
@@ -80,15 +123,14 @@ struct Builder {
     }
     int64_t count = (int64_t)D.tiles.size() - begin;
     int shared = 0;
-    if (top && D.world > 1 && flops >= D.shared_min_flops) {
+    if (multi && mode != 2 && flops >= D.shared_min_flops) {
       // split the tile list across the ranks; every rank builds the same list, keeps its slice
       int64_t lo = count * D.rank / D.world, hi = count * (D.rank + 1) / D.world;
       flops *= (double)(hi - lo) / (double)std::max<int64_t>(1, count);
       begin += lo, count = hi - lo;
       shared = 1;
     }
-    if (count > 0 || shared) D.launches.push_back(Launch{K_GEMM, level, phase, begin, count, flops, cfg, shared});
-    if (shared) D.launches.push_back(Launch{K_BARRIER, level, phase, 0, 0, 0, 0, 0});
+    push_launch(level, phase, cfg, begin, count, flops, shared);
   }
   // tile configuration is decided per launch: 128x128 tiles only pay when they fill the GPU
   void end_gemm(int level, int phase, bool top) {
@@ -222,8 +264,8 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
             }
             if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0, 0});
           }
-          // right-looking update of the rest of this block column (K = NB)
-          B.begin_gemm();
+          // right-looking update of the rest of this block column (K = NB); replicated on a shared top panel
+          B.begin_gemm(2);
           for (int h = h0; h < h1; h++) {
             int n = P.sz[h], ld = S.ld[h];
             if (n <= d0) continue;
@@ -241,18 +283,20 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           B.end_gemm(lvl, phase, top);
         }
         // right-looking update of everything to the right of block column J (K = NBO)
-        B.begin_gemm();
+        B.begin_gemm(1);
         for (int h = h0; h < h1; h++) {
           int n = P.sz[h], ld = S.ld[h];
           int c1 = c0 + NBO;
           if (n <= c1) continue;
           int64_t base = S.poff[h];
+          const int next_tc = (std::min(NBO, n - c1) + 63) / 64;  // tile columns of the next block column
           if (which != 1)
             B.add_problem(base + c1 + (int64_t)c1 * ld, ld, (which == 0 ? n : S.rows[h]) - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld,
-                          base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
+                          base + c1 + (int64_t)c0 * ld, ld, ld, NBO, c1 / 64, next_tc);
           else {
             int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
-            B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO);
+            B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO,
+                          r0 / 64, next_tc);
           }
         }
         B.end_gemm(lvl, phase, top);

@@ -23,6 +23,7 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["CHOL_SHARED_MIN_FLOPS"] = "1"   # split every top-level GEMM launch of this small grid
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cholesky_b200 import Cholesky
@@ -76,6 +77,9 @@ def test_partition_covers_single_rank_schedule(world):
     assert all(x == pytest.approx(repl[0], rel=1e-12) for x in repl)
     shared = sum(total(r["launches"], "gemm_grouped", "flops", lambda l: top(l) and l["shared"]) for r in ranks)
     assert shared + repl[0] == pytest.approx(total(single["launches"], "gemm_grouped", "flops", top), rel=1e-9)
+    # both split kinds are present: broadcast-stored tiles (1) and owner-local tiles (2)
+    kinds = {l["shared"] for r in ranks for l in r["launches"] if l["kind"] == "gemm_grouped" and top(l)}
+    assert 1 in kinds
     # one all-reduce of the top copies per rank, and a barrier after every shared launch
     for r in ranks:
         assert sum(l["kind"] == "allreduce_top" for l in r["launches"]) == 1
