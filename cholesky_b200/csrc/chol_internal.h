@@ -102,7 +102,7 @@ struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
   int ld, nb, rows, pad;
 };
 
-enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_BARRIER = 3, K_ALLREDUCE = 4 };
+enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_BARRIER = 3, K_ALLREDUCE = 4, K_NOP = 5 };
 enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
 struct Launch {
   int kind;
@@ -111,7 +111,9 @@ struct Launch {
   int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
   int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128, 2 = 128x64
-  int shared;            // multi-GPU: this rank runs a slice of the tiles and stores into every rank's copy
+  int shared;            // multi-GPU: 1 = this rank's tiles are stored into every rank's copy, 2 = owned tiles, local store
+  int stream;            // 0 = update stream, 1 = chain stream (look-ahead)
+  int wait_ev, rec_ev;   // event to wait for before / to record after the launch (-1: none)
 };
 
 struct Schedule {
@@ -134,6 +136,8 @@ struct Schedule {
   // multi-GPU partition (world = 2^depth ranks)
   int rank = 0, world = 1, depth = 0;
   bool split_phases = false;  // true: fused_dpotrf and fused_dtrsm as separate launch sequences (piecewise API)
+  bool lookahead = true;      // chain kernels on a second stream, overlapping the trailing updates (CHOL_LOOKAHEAD=0: off)
+  int num_events = 0;         // cross-stream events the launch list refers to
   int64_t top_doubles = 0;         // leading part of the factor buffer that holds the shared top panels
   double shared_min_flops = 2e9;   // top-level GEMM launches at least this large are split across ranks
 };

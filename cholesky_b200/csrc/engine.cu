@@ -42,7 +42,10 @@ struct chol {
   size_t h_pinned_bytes = 0;
   std::vector<double> h_fac;  // host copy of the factor, fetched lazily
   bool h_fac_valid = false;
-  double k_ms[5] = {0, 0, 0, 0, 0};
+  cudaStream_t stream1 = nullptr, cur = nullptr;  // chain stream (look-ahead); stream of the launch being issued
+  std::vector<cudaEvent_t> evs;                   // cross-stream events of the launch list
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double k_ms[6] = {0, 0, 0, 0, 0, 0};
   double k_gemm_flops = 0;
   std::vector<float> launch_ms;  // per launch, from the last instrumented pass
   // multi-GPU: one handle per rank; peers' factor buffers and flag words mapped through CUDA IPC
@@ -97,6 +100,13 @@ static void free_device(chol_t *c) {
   c->d_flags = nullptr, c->peers_ready = false;
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   c->h_pinned = nullptr, c->h_pinned_bytes = 0;
+  for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+  c->evs.clear();
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  c->ev_fork = c->ev_join = nullptr;
+  if (c->stream1) cudaStreamDestroy(c->stream1);
+  c->stream1 = nullptr;
   if (c->stream) cudaStreamDestroy(c->stream);
   c->device_ready = false;
 }
@@ -259,6 +269,10 @@ static int ensure_device(chol_t *c) {
   if (e != cudaSuccess || ndev == 0) return fail(c, "no CUDA device: the numeric factorization runs on the GPU only (no CPU fallback)");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream1, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  c->cur = c->stream;
   CK(cudaMalloc((void **)&c->d_fac, (size_t)c->S.total_doubles * sizeof(double)));
   c->device_ready = true;
   if (upload(c, &c->d_vals, c->P.ev)) return -100;
@@ -270,6 +284,7 @@ static int ensure_device(chol_t *c) {
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
+  CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
   CK(cudaMalloc((void **)&c->d_flags, kMaxPeers * sizeof(unsigned long long)));
   CK(cudaMemset(c->d_flags, 0, kMaxPeers * sizeof(unsigned long long)));
   c->peers.n = 1, c->peers.rank = 0;
@@ -304,10 +319,10 @@ static void launch_gemm(chol_t *c, const Launch &l) {
     attr[(l.shared == 1) ? 1 : 0] = true;
   }
   if (l.shared == 1)
-    gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+    gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
   else
-    gemm_grouped<BM, BN, BK, WM, WN, ST, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+    gemm_grouped<BM, BN, BK, WM, WN, ST, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
 }
 template <int BM, int BN, int BK, int WM, int WN, int ST, int MINB>
@@ -320,25 +335,25 @@ static void launch_gemm_ws(chol_t *c, const Launch &l) {
     attr[(l.shared == 1) ? 1 : 0] = true;
   }
   if (l.shared == 1)
-    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
   else
-    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
         c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
 }
 extern "C" {
 static void launch_barrier(chol_t *c) {
   c->epoch++;
-  peer_barrier<<<1, 32, 0, c->stream>>>(c->peers, c->epoch);
+  peer_barrier<<<1, 32, 0, c->cur>>>(c->peers, c->epoch);
 }
 
 static int run_launch(chol_t *c, const Launch &l) {
   switch (l.kind) {
     case K_POTRF:
-      potrf_tile<<<(unsigned)l.count, kNB, 0, c->stream>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
-      trsm_tile<<<(unsigned)l.count, kSlab, 0, c->stream>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      trsm_tile<<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
       if (l.count <= 0) break;
@@ -362,8 +377,10 @@ static int run_launch(chol_t *c, const Launch &l) {
       break;
     case K_ALLREDUCE:
       launch_barrier(c);
-      allreduce_top<<<148 * 4, 256, 0, c->stream>>>(c->peers, l.count / 2);
+      allreduce_top<<<148 * 4, 256, 0, c->cur>>>(c->peers, l.count / 2);
       launch_barrier(c);
+      break;
+    case K_NOP:
       break;
   }
   return 0;
@@ -374,17 +391,37 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   std::vector<cudaEvent_t> ev;
   std::vector<int> kinds;
   std::vector<double> fl;
+  // cross-stream events of the launch list (look-ahead); the chain stream starts after whatever is
+  // already queued on the main stream (assembly)
+  while ((int)c->evs.size() < c->D.num_events) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->evs.push_back(e);
+  }
+  if (c->D.lookahead) {
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->stream1, c->ev_fork, 0));
+  }
   for (const Launch &l : c->D.launches) {
-    if (l.level > lvl_from || l.level < lvl_to || !(l.phase & phase_mask)) continue;
+    if (l.level > lvl_from || l.level < lvl_to) continue;
+    if (l.kind != K_NOP && !(l.phase & phase_mask)) continue;
+    c->cur = l.stream ? c->stream1 : c->stream;
+    if (l.wait_ev >= 0) cudaStreamWaitEvent(c->cur, c->evs[l.wait_ev], 0);
     if (per_kernel_timing) {
       cudaEvent_t a, b;
       cudaEventCreate(&a), cudaEventCreate(&b);
-      cudaEventRecord(a, c->stream);
+      cudaEventRecord(a, c->cur);
       run_launch(c, l);
-      cudaEventRecord(b, c->stream);
+      cudaEventRecord(b, c->cur);
       ev.push_back(a), ev.push_back(b), kinds.push_back(l.kind), fl.push_back(l.flops);
     } else
       run_launch(c, l);
+    if (l.rec_ev >= 0) cudaEventRecord(c->evs[l.rec_ev], c->cur);
+  }
+  c->cur = c->stream;
+  if (c->D.lookahead) {  // partial runs (piecewise calls) may leave work on the chain stream: join it
+    CK(cudaEventRecord(c->ev_join, c->stream1));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   }
   CK(cudaGetLastError());
   if (per_kernel_timing) {
@@ -409,6 +446,13 @@ int chol_assemble(chol_t *c) {
   if (do_assemble(c)) return -1;
   CK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// kernels one step launches (the all-reduce is a barrier, the reduction kernel and a barrier)
+static int64_t count_kernels(chol_t *c) {
+  int64_t k = 0;
+  for (const Launch &l : c->D.launches) k += l.kind == K_NOP ? 0 : l.kind == K_ALLREDUCE ? 3 : (l.kind == K_GEMM && l.count <= 0) ? 0 : 1;
+  return k;
 }
 
 static int fetch_info(chol_t *c, int *info) {
@@ -452,7 +496,7 @@ int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
     st->seconds_last = secs.back();
     st->assemble_seconds = asm_s;
     st->flops = c->S.flops();
-    st->kernel_launches = (int64_t)c->D.launches.size();
+    st->kernel_launches = count_kernels(c);
     st->info = info;
   }
   if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
@@ -506,7 +550,7 @@ int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_o
     st->seconds_best = st->seconds_median = st->seconds_last = ms * 1e-3;
     st->assemble_seconds = 0;
     st->flops = c->S.flops();
-    st->kernel_launches = (int64_t)c->D.launches.size() + 2;
+    st->kernel_launches = count_kernels(c) + 2;
     st->info = info;
   }
   if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));

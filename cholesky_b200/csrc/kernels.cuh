@@ -319,110 +319,173 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
   }
 
   double *__restrict__ C = fac + pr.c_off;
+  if (!SHARED) {
+    // local destination: read-modify-write straight from the accumulator fragments (measured 2 % faster
+    // on one GPU than staging through shared memory)
 #pragma unroll
-  for (int i = 0; i < MB; i++) {
-    const int r = row0 + wm0 + i * 8 + g;
-    if (r >= pr.M) continue;
+    for (int i = 0; i < MB; i++) {
+      const int r = row0 + wm0 + i * 8 + g;
+      if (r >= pr.M) continue;
 #pragma unroll
-    for (int j = 0; j < NBk; j++) {
+      for (int j = 0; j < NBk; j++) {
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
-        if (cc < pr.N && (!pr.tri || r >= cc)) {
-          const size_t o = r + (size_t)cc * pr.ldc;
-          const double v = C[o] - acc[i][j][e];
-          if (SHARED) {
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; p++)
-              if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
-          } else
-            C[o] = v;
+        for (int e = 0; e < 2; e++) {
+          const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+          if (cc < pr.N && (!pr.tri || r >= cc)) C[r + (size_t)cc * pr.ldc] -= acc[i][j][e];
         }
       }
     }
+    return;
   }
-  if (SHARED) __threadfence_system();
+  // SHARED: the tile also goes to every peer's copy.  The accumulators are parked column-major in shared
+  // memory (stride BM + 2 keeps the fragment stores conflict-free), then every warp walks whole columns,
+  // lane = row, so the peer stores over NVLink are coalesced runs instead of 8-byte scatters.
+  constexpr int kLdC = BM + 2;
+  static_assert(BN * kLdC <= STAGES * Cfg::kStageDoubles, "C staging tile must fit in the stage ring");
+  asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kConsumers * 32) : "memory");  // all consumers are done with the ring
+  double *Cs = smem;
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NBk; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) Cs[(wn0 + j * 8 + 2 * t + e) * kLdC + wm0 + i * 8 + g] = acc[i][j][e];
+  asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kConsumers * 32) : "memory");
+  for (int j = warp; j < BN; j += Cfg::kConsumers) {
+    const int cc = col0 + j;
+    if (cc >= pr.N) break;
+#pragma unroll
+    for (int rr = lane; rr < BM; rr += 32) {
+      const int r = row0 + rr;
+      if (r < pr.M && (!pr.tri || r >= cc)) {
+        const size_t o = r + (size_t)cc * pr.ldc;
+        const double v = C[o] - Cs[j * kLdC + rr];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; p++)
+          if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
-// One thread per row, the tile in shared memory (row stride 65: conflict-free).  Left-looking by
-// column: all rows at or below the diagonal take their dot product with row k at once, thread k
-// turns its result into 1/sqrt, the others scale.  Compact loops on purpose: a fully unrolled
-// version is instruction-fetch bound.
-__global__ void __launch_bounds__(kNB) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac, int *__restrict__ info) {
+// Pivot tile in shared memory (row stride 65: conflict-free), blocked by 16 columns.  Inside a block:
+// left-looking by column with one thread per row (64 threads, named barrier) -- all rows at or below
+// the diagonal take their short dot product with row k at once, thread k turns its result into
+// 1/sqrt, the others scale.  After a block: rank-16 update of the trailing lower triangle by all 256
+// threads.  Compact loops on purpose: a fully unrolled version is instruction-fetch bound.
+constexpr int kPotrfThreads = 256;
+constexpr int kPB = 16;
+__global__ void __launch_bounds__(kPotrfThreads) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+                                                            int *__restrict__ info) {
   __shared__ double T[kNB][kNB + 1];
+  __shared__ double rk;  // 1 / L[k][k]
   const PotrfDesc d = descs[blockIdx.x];
   double *__restrict__ A = fac + d.off;
-  const int nb = d.nb, i = threadIdx.x;
-  for (int c0 = 0; c0 < nb; c0 += 8) {  // eight coalesced column loads in flight per thread
-    double v[8];
+  const int nb = d.nb, tid = threadIdx.x;
+  {  // thread (row i, column group cg) loads 16 columns, eight loads in flight
+    const int i = tid & (kNB - 1), cg = tid / kNB;
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = (i < nb && c0 + u <= i) ? A[i + (size_t)(c0 + u) * d.ld] : 0.0;
+    for (int h = 0; h < 2; h++) {
+      double v[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (c0 + u < kNB) T[i][c0 + u] = v[u];
+      for (int u = 0; u < 8; u++) {
+        const int c = cg * 16 + h * 8 + u;
+        v[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) T[i][cg * 16 + h * 8 + u] = v[u];
+    }
   }
   __syncthreads();
-  __shared__ double rk;  // 1 / L[k][k]
-  for (int k = 0; k < nb; k++) {
-    // every row at or below the diagonal takes its dot product with row k at the same time
-    double sk = 0.0;
-    if (i >= k && i < nb) {
-      double s0 = T[i][k], s1 = 0, s2 = 0, s3 = 0;
-      int j = 0;
-      for (; j + 7 < k; j += 8) {
-        double a0 = T[i][j], a1 = T[i][j + 1], a2 = T[i][j + 2], a3 = T[i][j + 3];
-        double a4 = T[i][j + 4], a5 = T[i][j + 5], a6 = T[i][j + 6], a7 = T[i][j + 7];
-        double b0 = T[k][j], b1 = T[k][j + 1], b2 = T[k][j + 2], b3 = T[k][j + 3];
-        double b4 = T[k][j + 4], b5 = T[k][j + 5], b6 = T[k][j + 6], b7 = T[k][j + 7];
-        s0 -= a0 * b0, s1 -= a1 * b1, s2 -= a2 * b2, s3 -= a3 * b3;
-        s0 -= a4 * b4, s1 -= a5 * b5, s2 -= a6 * b6, s3 -= a7 * b7;
+  for (int kb = 0; kb < nb; kb += kPB) {
+    const int kend = min(kb + kPB, nb);
+    if (tid < kNB) {
+      const int i = tid;
+      for (int k = kb; k < kend; k++) {
+        double sk = 0.0;
+        if (i >= k && i < nb) {
+          double s0 = T[i][k], s1 = 0.0;
+          int j = kb;
+          for (; j + 3 < k; j += 4) {
+            const double a0 = T[i][j], a1 = T[i][j + 1], a2 = T[i][j + 2], a3 = T[i][j + 3];
+            const double b0 = T[k][j], b1 = T[k][j + 1], b2 = T[k][j + 2], b3 = T[k][j + 3];
+            s0 -= a0 * b0, s1 -= a1 * b1, s0 -= a2 * b2, s1 -= a3 * b3;
+          }
+          for (; j < k; j++) s0 -= T[i][j] * T[k][j];
+          sk = s0 + s1;
+        }
+        if (i == k) {
+          if (!(sk > 0.0)) {
+            atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+            sk = 1.0;
+          }
+          const double r = rsqrt(sk);
+          T[k][k] = sk * r;
+          rk = r;
+        }
+        asm volatile("bar.sync 1, 64;\n" ::: "memory");
+        if (i > k && i < nb) T[i][k] = sk * rk;
+        asm volatile("bar.sync 1, 64;\n" ::: "memory");
       }
-      for (; j < k; j++) s0 -= T[i][j] * T[k][j];
-      sk = (s0 + s1) + (s2 + s3);
-    }
-    if (i == k) {
-      if (!(sk > 0.0)) {
-        atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-        sk = 1.0;
-      }
-      const double r = rsqrt(sk);
-      T[k][k] = sk * r;
-      rk = r;
     }
     __syncthreads();
-    if (i > k && i < nb) T[i][k] = sk * rk;
+    const int rem = nb - kend;
+    if (rem > 0) {  // T[i][j] -= sum_k T[i][k] T[j][k] over the block just factored, i >= j >= kend
+      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
+        const int i = kend + idx % rem, j = kend + idx / rem;
+        if (i < j) continue;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (int k = kb; k < kend; k += 2) {
+          s0 += T[i][k] * T[j][k];
+          if (k + 1 < kend) s1 += T[i][k + 1] * T[j][k + 1];
+        }
+        T[i][j] -= s0 + s1;
+      }
+    }
     __syncthreads();
   }
-  __syncthreads();
-  for (int c0 = 0; c0 < nb; c0 += 8) {
+  {
+    const int i = tid & (kNB - 1), cg = tid / kNB;
 #pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (i < nb && c0 + u <= i && c0 + u < nb) A[i + (size_t)(c0 + u) * d.ld] = T[i][c0 + u];
+    for (int u = 0; u < 16; u++) {
+      const int c = cg * 16 + u;
+      if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = T[i][c];
+    }
   }
 }
 
-// 128-row slab per CTA, one row per thread in registers.  L^T is staged in shared memory so that
-// the eight multipliers a thread needs for one k are contiguous (broadcast vector loads); columns
-// are solved eight at a time to keep eight independent FMA chains in flight.
+// 128-row slab per CTA, one row per thread.  The slab (k-major, so a warp reads consecutive words) and
+// L^T live in shared memory; columns are solved eight at a time with eight independent FMA chains, the
+// eight multipliers of one k come as four broadcast vector loads.  Loops are deliberately not fully
+// unrolled: the straight-line version was instruction-fetch bound.
 constexpr int kSlab = 128;
+constexpr int kTrsmSmemBytes = (kNB * kNB + kNB + kNB * kSlab) * 8;
 __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
                                                    double *__restrict__ fac) {
-  __shared__ __align__(16) double Lt[kNB][kNB];  // Lt[k][c] = L[c][k]
-  __shared__ double rdiag[kNB];
+  extern __shared__ __align__(16) double tsm[];
+  double(*Lt)[kNB] = reinterpret_cast<double(*)[kNB]>(tsm);             // Lt[k][c] = L[c][k]
+  double *rdiag = tsm + kNB * kNB;                                       // 1 / L[c][c]
+  double(*xs)[kSlab] = reinterpret_cast<double(*)[kSlab]>(rdiag + kNB);  // xs[c][row in slab]
   const TileRef tl = tiles[blockIdx.x];
   const TrsmDesc d = descs[tl.prob];
   const int slab = (int)tl.tr | ((int)tl.tc << 16);
-  const int tid = threadIdx.x, nb = d.nb;
+  const int tid = threadIdx.x, nb = d.nb, nb8 = (nb + 7) & ~7;
   const double *__restrict__ Lg = fac + d.l_off;
   const int row = slab * kSlab + tid;
   const bool live = row < d.rows;
   double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
-  double x[kNB];
+  for (int c0 = 0; c0 < nb8; c0 += 8) {
+    double v[8];
 #pragma unroll
-  for (int c = 0; c < kNB; c++) x[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+    for (int u = 0; u < 8; u++) v[u] = (live && c0 + u < nb) ? Bp[(size_t)(c0 + u) * d.ld] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) xs[c0 + u][tid] = v[u];
+  }
   {
     constexpr int PER = kNB * kNB / kSlab;
     double v[PER];
@@ -440,18 +503,17 @@ __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ 
   }
   __syncthreads();
   if (!live) return;
-#pragma unroll
-  for (int cb = 0; cb < kNB; cb += 8) {
+  for (int cb = 0; cb < nb8; cb += 8) {
     double s[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) s[j] = x[cb + j];
-#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = xs[cb + j][tid];
+#pragma unroll 4
     for (int k = 0; k < cb; k++) {
-      const double xk = x[k];
+      const double xk = xs[k][tid];
       const double2 *l2 = reinterpret_cast<const double2 *>(&Lt[k][cb]);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        double2 l = l2[j];
+        const double2 l = l2[j];
         s[2 * j] -= xk * l.x;
         s[2 * j + 1] -= xk * l.y;
       }
@@ -459,13 +521,17 @@ __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ 
 #pragma unroll
     for (int j = 0; j < 8; j++) {
 #pragma unroll
-      for (int jj = 0; jj < j; jj++) s[j] -= x[cb + jj] * Lt[cb + jj][cb + j];
-      x[cb + j] = s[j] * rdiag[cb + j];
+      for (int jj = 0; jj < j; jj++) s[j] -= s[jj] * Lt[cb + jj][cb + j];
+      s[j] *= rdiag[cb + j];
     }
-  }
 #pragma unroll
-  for (int c = 0; c < kNB; c++)
-    if (c < nb) Bp[(size_t)c * d.ld] = x[c];
+    for (int j = 0; j < 8; j++) xs[cb + j][tid] = s[j];
+  }
+  for (int c0 = 0; c0 < nb; c0 += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < nb) Bp[(size_t)(c0 + u) * d.ld] = xs[c0 + u][tid];
+  }
 }
 
 __global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *__restrict__ offs, int64_t nz, double *__restrict__ fac) {

@@ -5,19 +5,25 @@
 //   (a) fused_dpotrf  -> blocked Cholesky of every pivot block of the level, in lock step:
 //                        NBO-wide block columns; inside one, NB-wide tiles (tile POTRF, slab TRSM,
 //                        small trailing GEMM); after one, a right-looking grouped GEMM (K = NBO) over
-//                        the whole trailing pivot block, which keeps the GPU full even for one front.
-//   (b) fused_dtrsm   -> the same blocking applied to the filled off-diagonal rows of the panels.
+//                        the whole trailing panel, which keeps the GPU full even for one front.
+//   (b) fused_dtrsm   -> the same blocking applied to the filled off-diagonal rows of the panels
+//                        (by default fused with (a): every row below a pivot tile advances together).
 //   (c) fused_dsyrk / fused_dgemm -> one grouped GEMM over DESTINATION clusters: every filled
 //                        cluster (g, p, ia, jb) owns the ordered list of its contributors
 //                        (s ascending), so accumulation is atomic-free and deterministic; the
 //                        extend-add index map is the precomputed destination offset.
 //
+// Look-ahead: the latency-bound chain of a block column (tile POTRF, slab TRSM, K = NB GEMM) runs on
+// a second stream.  The trailing update of block column J is split into the tiles of block column
+// J + 1 (part A) and the rest (part B); the chain of J + 1 only waits for A, so it overlaps B.
+//
 // Multi-GPU (world = 2^d ranks, one process per GPU): rank r owns the subtree under heap index
 // 2^d + r and schedules only its separators on levels >= d.  Its Schur contributions to the top
 // d levels land in its own copy of the top panels; one K_ALLREDUCE sums the copies over NVLink.
-// On the top levels every rank runs the small kernels redundantly (bit-identical), while the large
-// grouped GEMMs are split by tiles across the ranks, each rank storing its tiles into every
-// rank's copy (shared launches), followed by a K_BARRIER.
+// On the top levels every rank runs the chain redundantly (bit-identical).  Trailing updates use a
+// static ownership of tile rows (row tile index mod world): part A is stored into every rank's
+// copy (SHARED kernel) and followed by a K_BARRIER, part B stays local until its block column's turn.
+// Schur updates of top levels are split by contiguous tile slices and stored into every copy.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -34,17 +40,43 @@ struct Builder {
   Schedule &D;
   Builder(const Problem &p, const Symbolic &s, Schedule &d) : P(p), S(s), D(d) {}
 
+  // ---- launches, streams and events
+  int last[2] = {-1, -1};   // index of the last launch pushed on each stream
+  int pendw[2] = {-1, -1};  // event the next launch of the stream has to wait for
+  static Launch mk(int kind, int level, int phase, int64_t begin, int64_t count, double flops, int cfg, int shared) {
+    Launch l;
+    l.kind = kind, l.level = level, l.phase = phase, l.begin = begin, l.count = count, l.flops = flops, l.cfg = cfg, l.shared = shared;
+    l.stream = 0, l.wait_ev = -1, l.rec_ev = -1;
+    return l;
+  }
+  void push(Launch l, int stream) {
+    if (!D.lookahead) stream = 0;
+    l.stream = stream;
+    l.wait_ev = pendw[stream];
+    pendw[stream] = -1;
+    D.launches.push_back(l);
+    last[stream] = (int)D.launches.size() - 1;
+  }
+  // everything pushed so far on stream `src` happens before whatever is pushed next on stream `dst`
+  void depend(int dst, int src) {
+    if (!D.lookahead || dst == src || last[src] < 0) return;
+    if (D.launches[last[src]].rec_ev < 0) D.launches[last[src]].rec_ev = D.num_events++;
+    const int ev = D.launches[last[src]].rec_ev;
+    if (pendw[dst] >= 0 && pendw[dst] != ev) push(mk(K_NOP, D.launches[last[src]].level, 0, 0, 0, 0, 0, 0), dst);
+    pendw[dst] = ev;
+  }
+
+  // ---- grouped GEMM launches
   struct Pending {
     int prob;
     double flops;
-    // in-panel right-looking update of a shared top panel: tile rows are owned by rank
-    // (row_tile0 + tr) % world for the whole panel factorization, so a tile is only stored locally
-    // until it belongs to the next block column (tile columns < bcast_tc), which every rank needs
+    // trailing update of a panel: tile rows are owned by rank (row_tile0 + tr) % world for the whole
+    // panel factorization; tile columns < bcast_tc belong to the next block column (part A)
     int row_tile0 = -1, bcast_tc = 0;
   };
   std::vector<Pending> pend;
-  int mode = 0;  // 0: ordinary launch; 1: in-panel block-column update (owned tiles); 2: never split
-  void begin_gemm(int m = 0) {
+  int mode = 0;  // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = NB)
+  void begin_gemm(int m) {
     pend.clear();
     mode = m;
   }
@@ -69,25 +101,26 @@ struct Builder {
     g.contrib_begin = (int)D.contribs.size(), g.contrib_count = 1;
     D.contribs.push_back(GemmContrib{a_off, b_off, lda, ldb, K, 0});
     D.probs.push_back(g);
-    // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
     Pending pd;
     pd.prob = (int)D.probs.size() - 1;
+    // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
     pd.flops = 2.0 * K * ((double)M * N - (tri ? 0.5 * N * (N - 1.0) : 0.0));
     pd.row_tile0 = row_tile0, pd.bcast_tc = bcast_tc;
     pend.push_back(pd);
   }
-  void push_launch(int level, int phase, int cfg, int64_t begin, int64_t count, double flops, int shared) {
-    if (count > 0 || shared == 1) D.launches.push_back(Launch{K_GEMM, level, phase, begin, count, flops, cfg, shared});
-    if (shared == 1) D.launches.push_back(Launch{K_BARRIER, level, phase, 0, 0, 0, 0, 0});
+  void push_gemm(int level, int phase, int cfg, int64_t begin, int64_t count, double flops, int shared, int stream) {
+    if (count > 0 || shared == 1) push(mk(K_GEMM, level, phase, begin, count, flops, cfg, shared), stream);
+    if (shared == 1) push(mk(K_BARRIER, level, phase, 0, 0, 0, 0, 0), stream);
   }
   void emit(int level, int phase, int cfg, const std::vector<Pending> &list, bool top) {
     if (list.empty()) return;
     const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
     const bool multi = top && D.world > 1;
-    if (multi && mode == 1 && cfg == 0) {
-      // owned tiles: the next block column's tiles are stored into every rank's copy, the rest locally
+    if (mode == 1 && cfg == 0) {
+      // part A: the next block column's tiles (in multi-GPU mode stored into every rank's copy);
+      // part B: the rest of the trailing panel (local).  Tile rows have a static owner.
       double all_tiles = 0, flops = 0;
-      std::vector<TileRef> bc, loc;
+      std::vector<TileRef> pa, pb;
       for (const Pending &pd : list) {
         const GemmProblem &g = D.probs[pd.prob];
         int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
@@ -95,18 +128,20 @@ struct Builder {
           for (int tr = 0; tr < tr_n; tr++) {
             if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;
             all_tiles += 1;
-            if ((pd.row_tile0 + tr) % D.world != D.rank) continue;
-            (tc < pd.bcast_tc ? bc : loc).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+            if (multi && (pd.row_tile0 + tr) % D.world != D.rank) continue;
+            (tc < pd.bcast_tc ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
           }
         flops += pd.flops;
       }
       const double per_tile = flops / std::max(1.0, all_tiles);
+      depend(0, 1);  // the chain of this block column is done
       int64_t b0 = (int64_t)D.tiles.size();
-      D.tiles.insert(D.tiles.end(), bc.begin(), bc.end());
-      push_launch(level, phase, cfg, b0, (int64_t)bc.size(), per_tile * (double)bc.size(), 1);
+      D.tiles.insert(D.tiles.end(), pa.begin(), pa.end());
+      push_gemm(level, phase, cfg, b0, (int64_t)pa.size(), per_tile * (double)pa.size(), multi ? 1 : 0, 0);
+      depend(1, 0);  // the next chain may start as soon as part A is in place
       int64_t b1 = (int64_t)D.tiles.size();
-      D.tiles.insert(D.tiles.end(), loc.begin(), loc.end());
-      push_launch(level, phase, cfg, b1, (int64_t)loc.size(), per_tile * (double)loc.size(), 2);
+      D.tiles.insert(D.tiles.end(), pb.begin(), pb.end());
+      push_gemm(level, phase, cfg, b1, (int64_t)pb.size(), per_tile * (double)pb.size(), multi ? 2 : 0, 0);
       return;
     }
     int64_t begin = (int64_t)D.tiles.size();
@@ -130,9 +165,11 @@ struct Builder {
       begin += lo, count = hi - lo;
       shared = 1;
     }
-    push_launch(level, phase, cfg, begin, count, flops, shared);
+    const int stream = mode == 2 ? 1 : 0;
+    if (stream == 0) depend(0, 1);
+    push_gemm(level, phase, cfg, begin, count, flops, shared, stream);
   }
-  // tile configuration is decided per launch: 128x128 tiles only pay when they fill the GPU
+  // tile configuration is decided per launch: larger tiles only pay when they fill the GPU
   void end_gemm(int level, int phase, bool top) {
     int64_t n128 = 0;
     for (const Pending &pd : pend)
@@ -168,9 +205,11 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
   if (depth >= P.levels) return err = "more ranks than subtrees", -1;
   D.depth = depth;
-  if (const char *e = getenv("CHOL_BIG_CFG")) D.big_cfg = atoi(e);  // tuning knob: 1 = 128x128, 2 = 128x64
-  if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);  // tuning knob
+  if (const char *e = getenv("CHOL_BIG_CFG")) D.big_cfg = atoi(e);                    // tuning knob: 1 = 128x128, 2 = 128x64
+  if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);        // tuning knob
   if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
+  if (const char *e = getenv("CHOL_LOOKAHEAD")) D.lookahead = atoi(e) != 0;
+  if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
   const int NB = D.nb, NBO = D.nbo, SLAB = D.slab;
   Builder B(P, S, D);
@@ -229,6 +268,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     int maxn = 0;
     for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
     const int nouter = (maxn + NBO - 1) / NBO;
+    B.depend(1, 0);  // the chain of this level starts after the previous level's updates
 
     // which == 0: pivot blocks (rows [0, n));  which == 1: off-diagonal rows [r0, R);  which == 2: both at
     // once (rows [0, R)): the default, it halves the number of dependent small launches.  The split form
@@ -247,7 +287,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
               if (n <= d0) continue;
               D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
             }
-            if ((int64_t)D.potrf.size() > b) D.launches.push_back(Launch{K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0, 0});
+            if ((int64_t)D.potrf.size() > b) B.push(Builder::mk(K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0, 0), 1);
           }
           {
             int64_t b = (int64_t)D.trsm_tiles.size();
@@ -262,7 +302,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
               int ns = (rend - rbeg + SLAB - 1) / SLAB;
               for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
             }
-            if ((int64_t)D.trsm_tiles.size() > b) D.launches.push_back(Launch{K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0, 0});
+            if ((int64_t)D.trsm_tiles.size() > b) B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0, 0), 1);
           }
           // right-looking update of the rest of this block column (K = NB); replicated on a shared top panel
           B.begin_gemm(2);
@@ -330,7 +370,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
       if (x.crow != y.crow) return x.crow < y.crow;
       return x.hs < y.hs;
     });
-    B.begin_gemm();
+    B.begin_gemm(0);
     for (size_t i = 0; i < pairs.size();) {
       size_t j = i;
       while (j < pairs.size() && pairs[j].p == pairs[i].p && pairs[j].ccol == pairs[i].ccol && pairs[j].crow == pairs[i].crow) j++;
@@ -346,14 +386,22 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
         pf += 2.0 * pairs[c].K * ((double)q.M * q.N - (q.tri ? 0.5 * q.N * (q.N - 1.0) : 0.0));
       }
       D.probs.push_back(g);
-      B.pend.push_back(Builder::Pending{(int)D.probs.size() - 1, pf});
+      Builder::Pending pd;
+      pd.prob = (int)D.probs.size() - 1, pd.flops = pf;
+      B.pend.push_back(pd);
       i = j;
     }
     B.end_gemm(lvl, PH_UPDATE, top);
 
     // the subtrees are done: sum every rank's copy of the top panels before the top is factored
-    if (world > 1 && lvl == depth) D.launches.push_back(Launch{K_ALLREDUCE, lvl, PH_UPDATE, 0, D.top_doubles, 0, 0, 0});
+    if (world > 1 && lvl == depth) {
+      B.depend(0, 1);
+      B.push(Builder::mk(K_ALLREDUCE, lvl, PH_UPDATE, 0, D.top_doubles, 0, 0, 0), 0);
+    }
   }
+  // the step ends on stream 0
+  B.depend(0, 1);
+  if (B.pendw[0] >= 0) B.push(Builder::mk(K_NOP, 0, 0, 0, 0, 0, 0, 0), 0);
   if (D.contribs.size() > 0x7fffffffULL || D.probs.size() > 0x7fffffffULL) return err = "schedule too large", -1;
   return 0;
 }

