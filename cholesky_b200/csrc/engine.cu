@@ -14,12 +14,16 @@
 #include "../../include/cholesky.h"
 #include "chol_internal.h"
 #include "kernels.cuh"
+#include "solve.h"
+#include "solve_kernels.cuh"
 
 using namespace chb;
 
 
+struct SolveDev;
 struct chol {
   std::string err;
+  SolveDev *solve = nullptr;  // solve schedule and buffers, built on first use
   int device = 0;
   Problem P;
   Symbolic S;
@@ -88,8 +92,10 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   return 0;
 }
 
+static void free_solve(chol_t *c);
 static void free_device(chol_t *c) {
   if (!c->device_ready) return;
+  free_solve(c);
   cudaSetDevice(c->device);
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
   cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_info);
@@ -269,7 +275,12 @@ static int ensure_device(chol_t *c) {
   if (e != cudaSuccess || ndev == 0) return fail(c, "no CUDA device: the numeric factorization runs on the GPU only (no CPU fallback)");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->stream1, cudaStreamNonBlocking));
+  {  // the chain stream gets the highest priority: its few CTAs must slip in between the CTAs of a
+     // trailing update that fills the GPU, not queue behind them
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->stream1, cudaStreamNonBlocking, hi));
+  }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->cur = c->stream;
@@ -405,8 +416,9 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   for (const Launch &l : c->D.launches) {
     if (l.level > lvl_from || l.level < lvl_to) continue;
     if (l.kind != K_NOP && !(l.phase & phase_mask)) continue;
-    c->cur = l.stream ? c->stream1 : c->stream;
-    if (l.wait_ev >= 0) cudaStreamWaitEvent(c->cur, c->evs[l.wait_ev], 0);
+    // the instrumented pass runs everything on one stream so that an event pair brackets one kernel alone
+    c->cur = (l.stream && !per_kernel_timing) ? c->stream1 : c->stream;
+    if (l.wait_ev >= 0 && !per_kernel_timing) cudaStreamWaitEvent(c->cur, c->evs[l.wait_ev], 0);
     if (per_kernel_timing) {
       cudaEvent_t a, b;
       cudaEventCreate(&a), cudaEventCreate(&b);
@@ -416,7 +428,7 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
       ev.push_back(a), ev.push_back(b), kinds.push_back(l.kind), fl.push_back(l.flops);
     } else
       run_launch(c, l);
-    if (l.rec_ev >= 0) cudaEventRecord(c->evs[l.rec_ev], c->cur);
+    if (l.rec_ev >= 0 && !per_kernel_timing) cudaEventRecord(c->evs[l.rec_ev], c->cur);
   }
   c->cur = c->stream;
   if (c->D.lookahead) {  // partial runs (piecewise calls) may leave work on the chain stream: join it
@@ -773,52 +785,83 @@ int chol_residual(chol_t *c, int k, uint64_t seed, double *rel) {
   return 0;
 }
 
-// ------------------------------------------------------------------------------ solve (host substitution over the GPU factor)
+// ------------------------------------------------------------------------------ solve on the GPU
+}  // extern "C"
+struct SolveDev {
+  bool ready = false;
+  SolveSchedule V;
+  SolveTile *tiles = nullptr;
+  SolveGemv *gemv = nullptr;
+  TileRef *gemv_tiles = nullptr, *pull_tiles = nullptr, *gather_tiles = nullptr;
+  PullDest *pull = nullptr;
+  PullContrib *pull_contrib = nullptr;
+  GatherDesc *gather = nullptr;
+  int *rowmap = nullptr, *perm = nullptr;
+  double *x = nullptr, *io = nullptr;
+};
+static void free_solve(chol_t *c) {
+  SolveDev *v = c->solve;
+  if (!v) return;
+  cudaFree(v->tiles), cudaFree(v->gemv), cudaFree(v->gemv_tiles), cudaFree(v->pull_tiles), cudaFree(v->gather_tiles);
+  cudaFree(v->pull), cudaFree(v->pull_contrib), cudaFree(v->gather), cudaFree(v->rowmap), cudaFree(v->perm), cudaFree(v->x), cudaFree(v->io);
+  delete v;
+  c->solve = nullptr;
+}
+static int ensure_solve(chol_t *c) {
+  if (c->solve && c->solve->ready) return 0;
+  free_solve(c);
+  SolveDev *v = c->solve = new SolveDev();
+  if (build_solve(c->P, c->S, v->V, c->err)) return -1;
+  if (upload(c, &v->tiles, v->V.tiles) || upload(c, &v->gemv, v->V.gemv) || upload(c, &v->gemv_tiles, v->V.gemv_tiles) ||
+      upload(c, &v->pull, v->V.pull) || upload(c, &v->pull_contrib, v->V.pull_contrib) || upload(c, &v->pull_tiles, v->V.pull_tiles) ||
+      upload(c, &v->gather, v->V.gather) || upload(c, &v->gather_tiles, v->V.gather_tiles) || upload(c, &v->rowmap, v->V.rowmap) ||
+      upload(c, &v->perm, c->P.perm))
+    return -100;
+  CK(cudaMalloc((void **)&v->x, std::max(1, c->P.n) * sizeof(double)));
+  CK(cudaMalloc((void **)&v->io, std::max(1, c->P.n) * sizeof(double)));
+  v->ready = true;
+  return 0;
+}
+extern "C" {
+
+/* mmat.rg:1364-1495: permute b, forward substitution leaves -> root, backward root -> leaves, un-permute.
+ * Every step is a CUDA kernel on the factor as it sits in HBM (csrc/solve_kernels.cuh). */
 int chol_solve(chol_t *c, const double *b, double *x) {
-  if (fetch_factor(c)) return -1;
-  const Problem &P = c->P;
-  const Symbolic &S = c->S;
-  std::vector<double> v((size_t)P.n);
-  for (int p = 0; p < P.n; p++) v[p] = b[P.perm[p]];
-  // forward: leaves to root (mmat.rg:1394-1435)
-  for (int lvl = P.levels - 1; lvl >= 0; lvl--)
-    for (int hs = 1 << lvl; hs < (1 << (lvl + 1)); hs++) {
-      const double *pan = c->h_fac.data() + S.poff[hs];
-      int ld = S.ld[hs], n = P.sz[hs];
-      double *vs = v.data() + P.start[hs];
-      for (int j = 0; j < n; j++) {
-        vs[j] /= pan[j + (size_t)j * ld];
-        for (int i = j + 1; i < n; i++) vs[i] -= pan[i + (size_t)j * ld] * vs[j];
-      }
-      for (int64_t sgi = S.seg_ptr[hs] + 1; sgi < S.seg_ptr[hs + 1]; sgi++) {
-        const Seg &sg = S.segs[sgi];
-        double *vp = v.data() + P.start[sg.anc] + sg.lo;
-        for (int j = 0; j < n; j++)
-          for (int r = 0; r < sg.hi - sg.lo; r++) vp[r] -= pan[sg.off + r + (size_t)j * ld] * vs[j];
-      }
+  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+  if (c->world > 1) return fail(c, "chol_solve runs on a single-GPU handle (the factor of a partitioned run is distributed)");
+  if (ensure_solve(c)) return -1;
+  SolveDev *v = c->solve;
+  const int n = c->P.n;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
+  for (const SolveLaunch &l : v->V.launches) {
+    const unsigned g = (unsigned)l.count;
+    switch (l.kind) {
+      case SK_TILE_F:
+        solve_tile<false><<<g, kSolveNB, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        break;
+      case SK_TILE_B:
+        solve_tile<true><<<g, kSolveNB, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        break;
+      case SK_GEMV_F:
+        solve_gemv_fwd<<<g, kSolveSlab, 0, st>>>(v->gemv, v->gemv_tiles + l.begin, c->d_fac, v->x);
+        break;
+      case SK_GEMV_B:
+        solve_gemv_bwd<<<g, kSolveColG * 32, 0, st>>>(v->gemv, v->gemv_tiles + l.begin, c->d_fac, v->x);
+        break;
+      case SK_PULL:
+        solve_pull<<<g, kSolveSlab, 0, st>>>(v->pull, v->pull_contrib, v->pull_tiles + l.begin, c->d_fac, v->x);
+        break;
+      case SK_GATHER:
+        solve_gather<<<g, kSolveColG * 32, 0, st>>>(v->gather, v->gather_tiles + l.begin, v->rowmap, c->d_fac, v->x);
+        break;
     }
-  // backward: root to leaves (mmat.rg:1437-1479)
-  for (int lvl = 0; lvl < P.levels; lvl++)
-    for (int hs = 1 << lvl; hs < (1 << (lvl + 1)); hs++) {
-      const double *pan = c->h_fac.data() + S.poff[hs];
-      int ld = S.ld[hs], n = P.sz[hs];
-      double *vs = v.data() + P.start[hs];
-      for (int64_t sgi = S.seg_ptr[hs] + 1; sgi < S.seg_ptr[hs + 1]; sgi++) {
-        const Seg &sg = S.segs[sgi];
-        const double *vp = v.data() + P.start[sg.anc] + sg.lo;
-        for (int j = 0; j < n; j++) {
-          double acc = 0;
-          for (int r = 0; r < sg.hi - sg.lo; r++) acc += pan[sg.off + r + (size_t)j * ld] * vp[r];
-          vs[j] -= acc;
-        }
-      }
-      for (int j = n - 1; j >= 0; j--) {
-        double acc = vs[j];
-        for (int i = j + 1; i < n; i++) acc -= pan[i + (size_t)j * ld] * vs[i];
-        vs[j] = acc / pan[j + (size_t)j * ld];
-      }
-    }
-  for (int p = 0; p < P.n; p++) x[P.perm[p]] = v[p];
+  }
+  permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->x, v->perm, n, v->io);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(x, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -209,6 +209,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);        // tuning knob
   if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   if (const char *e = getenv("CHOL_LOOKAHEAD")) D.lookahead = atoi(e) != 0;
+  if (const char *e = getenv("CHOL_NBO")) D.nbo = std::max(64, atoi(e) / 64 * 64);  // tuning knob: block-column width
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
   const int NB = D.nb, NBO = D.nbo, SLAB = D.slab;

@@ -1,0 +1,127 @@
+// Solve schedule: forward substitution leaves -> root, backward root -> leaves (mmat.rg:1394-1479),
+// blocked by 64 columns inside a pivot block, all separators of a tree level in lock step.
+#include "solve.h"
+
+#include <algorithm>
+
+namespace chb {
+
+namespace {
+constexpr int NB = 64, SLAB = 128, COLG = 8;
+
+struct SegRef {
+  int grow;  // global permuted row of the segment start
+  int rows;
+  int h;
+  int64_t p_off;
+  int ld, K, x0;
+};
+}  // namespace
+
+int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::string &err) {
+  V = SolveSchedule();
+  const int L = P.levels;
+  // row map of the off-diagonal part of every panel
+  std::vector<int64_t> map_off(P.N + 2, 0);
+  for (int h = 1; h <= P.N; h++) {
+    const int n = P.sz[h], r0 = (n + 1) / 2 * 2;
+    map_off[h] = (int64_t)V.rowmap.size();
+    V.rowmap.resize(V.rowmap.size() + (size_t)std::max(0, S.rows[h] - r0), -1);
+    for (int64_t s = S.seg_ptr[h] + 1; s < S.seg_ptr[h + 1]; s++) {
+      const Seg &sg = S.segs[s];
+      for (int r = 0; r < sg.hi - sg.lo; r++) V.rowmap[map_off[h] + (sg.off - r0) + r] = P.start[sg.anc] + sg.lo + r;
+    }
+  }
+  auto add_gemv = [&](const SolveGemv &g) {
+    V.gemv.push_back(g);
+    return (int)V.gemv.size() - 1;
+  };
+
+  // ---- forward: leaves to root
+  std::vector<SegRef> refs;
+  for (int lvl = L - 1; lvl >= 0; lvl--) {
+    const int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    int maxn = 0;
+    for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
+    for (int d0 = 0; d0 < maxn; d0 += NB) {
+      int64_t b = (int64_t)V.tiles.size();
+      for (int h = h0; h < h1; h++) {
+        int n = P.sz[h];
+        if (n <= d0) continue;
+        V.tiles.push_back(SolveTile{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
+      }
+      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_F, b, (int64_t)V.tiles.size() - b});
+      int64_t gb = (int64_t)V.gemv_tiles.size();
+      for (int h = h0; h < h1; h++) {
+        int n = P.sz[h], ld = S.ld[h];
+        if (n <= d0) continue;
+        int dw = std::min(NB, n - d0), rows = n - (d0 + dw);
+        if (rows <= 0) continue;
+        int g = add_gemv(SolveGemv{S.poff[h] + (d0 + dw) + (int64_t)d0 * ld, ld, rows, dw, P.start[h] + d0, P.start[h] + d0 + dw, 0});
+        for (int s = 0; s < (rows + SLAB - 1) / SLAB; s++) V.gemv_tiles.push_back(TileRef{g, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
+      }
+      if ((int64_t)V.gemv_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GEMV_F, gb, (int64_t)V.gemv_tiles.size() - gb});
+    }
+    // ancestors pull the level's contributions: all segments that hit one ancestor row cluster
+    refs.clear();
+    for (int h = h0; h < h1; h++)
+      for (int64_t s = S.seg_ptr[h] + 1; s < S.seg_ptr[h + 1]; s++) {
+        const Seg &sg = S.segs[s];
+        refs.push_back(SegRef{P.start[sg.anc] + sg.lo, sg.hi - sg.lo, h, S.poff[h] + sg.off, S.ld[h], P.sz[h], P.start[h]});
+      }
+    std::sort(refs.begin(), refs.end(), [](const SegRef &a, const SegRef &b) { return a.grow != b.grow ? a.grow < b.grow : a.h < b.h; });
+    int64_t pb = (int64_t)V.pull_tiles.size();
+    for (size_t i = 0; i < refs.size();) {
+      size_t j = i;
+      while (j < refs.size() && refs[j].grow == refs[i].grow) j++;
+      PullDest d{refs[i].grow, refs[i].rows, (int)V.pull_contrib.size(), (int)(j - i)};
+      for (size_t c = i; c < j; c++) {
+        if (refs[c].rows != refs[i].rows) return err = "internal: solve contributors disagree on a cluster's size", -1;
+        V.pull_contrib.push_back(PullContrib{refs[c].p_off, refs[c].ld, refs[c].K, refs[c].x0, 0});
+      }
+      V.pull.push_back(d);
+      for (int s = 0; s < (d.rows + SLAB - 1) / SLAB; s++) V.pull_tiles.push_back(TileRef{(int)V.pull.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
+      i = j;
+    }
+    if ((int64_t)V.pull_tiles.size() > pb) V.launches.push_back(SolveLaunch{SK_PULL, pb, (int64_t)V.pull_tiles.size() - pb});
+  }
+
+  // ---- backward: root to leaves
+  for (int lvl = 0; lvl < L; lvl++) {
+    const int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    int maxn = 0;
+    for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
+    int64_t gb = (int64_t)V.gather_tiles.size();
+    for (int h = h0; h < h1; h++) {
+      const int n = P.sz[h], r0 = (n + 1) / 2 * 2, nrows = S.rows[h] - r0;
+      if (nrows <= 0 || n <= 0) continue;
+      V.gather.push_back(GatherDesc{S.poff[h] + r0, map_off[h], S.ld[h], nrows, n, P.start[h]});
+      for (int g = 0; g < (n + COLG - 1) / COLG; g++) V.gather_tiles.push_back(TileRef{(int)V.gather.size() - 1, (uint16_t)(g & 0xffff), (uint16_t)(g >> 16)});
+    }
+    if ((int64_t)V.gather_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GATHER, gb, (int64_t)V.gather_tiles.size() - gb});
+    const int nblk = (maxn + NB - 1) / NB;
+    for (int blk = nblk - 1; blk >= 0; blk--) {
+      const int d0 = blk * NB;
+      int64_t b = (int64_t)V.tiles.size();
+      for (int h = h0; h < h1; h++) {
+        int n = P.sz[h];
+        if (n <= d0) continue;
+        V.tiles.push_back(SolveTile{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
+      }
+      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_B, b, (int64_t)V.tiles.size() - b});
+      if (d0 == 0) continue;
+      int64_t tb = (int64_t)V.gemv_tiles.size();
+      for (int h = h0; h < h1; h++) {
+        int n = P.sz[h], ld = S.ld[h];
+        if (n <= d0) continue;
+        int dw = std::min(NB, n - d0);
+        int g = add_gemv(SolveGemv{S.poff[h] + d0, ld, d0, dw, P.start[h] + d0, P.start[h], 0});
+        for (int s = 0; s < (d0 + COLG - 1) / COLG; s++) V.gemv_tiles.push_back(TileRef{g, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
+      }
+      if ((int64_t)V.gemv_tiles.size() > tb) V.launches.push_back(SolveLaunch{SK_GEMV_B, tb, (int64_t)V.gemv_tiles.size() - tb});
+    }
+  }
+  return 0;
+}
+
+}  // namespace chb

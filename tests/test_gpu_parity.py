@@ -91,6 +91,10 @@ def test_generated_grids_match_oracle(grid, tmp_path):
     scale = np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max())
     assert np.max(np.abs(got - ref) / scale) <= 1e-10
     assert ch.residual(k=8) <= 1e-12
+    # solve on the GPU (forward / backward sweeps over the panels) against the oracle's dtrsv/dgemv sweep
+    b = np.random.default_rng(0).integers(1, 11, size=ch.n).astype(np.float64)
+    x, xo = ch.solve(b), o.solve(b)
+    assert np.max(np.abs(x - xo)) <= 1e-10 * np.max(np.abs(xo))
 
 
 def test_large_front_blocking_paths(tmp_path):
