@@ -226,7 +226,10 @@ def main():
             "gpu_launches": int(st.kernel_launches) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_grouped (FP64 DMMA)", "achieved": gemm_tf, "peak": peak,
-                         "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_how,
+                         "unit": "TFLOP/s", "frac": gemm_tf / peak,
+                         # DRAM bytes of ONE captured launch of this kernel (ncu --set full, the level-3 Schur update of
+                         # the 64^3 grid, 7.19e10 flops, profiles/ncu_gemm_grouped_ws_r01.txt); the tensor pipe bounds it
+                         "traffic": 866438144, "peak_source": peak_how,
                          "kernel_share_of_step": kt["gemm_ms"] / tot_ms if tot_ms else None,
                          "kernel_ms": {k: kt[k] for k in ("potrf_ms", "trsm_ms", "gemm_ms")}},
             "factor": {"n": ch.n, "nz": ch.nz, "levels": ch.levels, "flops": flops, "factor_GiB": ch.factor_doubles() * 8 / 2**30,
