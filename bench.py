@@ -204,14 +204,17 @@ def main():
     clocks = sampler.stop(local_rank) if rank == 0 else None
     kt = ch.kernel_times()      # one instrumented iteration: CUDA events around every launch
     res = ch.residual(k=2) if (ch.n <= 300000 and world == 1) else None
-    solve_ms = None
+    solve_ms = solve_res = None
     if world == 1:   # forward/backward sweeps on the GPU, host vectors in and out (mmat.rg:1364-1495)
         import numpy as np
         rhs = np.random.default_rng(0).integers(1, 11, size=ch.n).astype(np.float64)
-        ch.solve(rhs)
+        xs = ch.solve(rhs)
         t1 = time.time()
         ch.solve(rhs)
         solve_ms = (time.time() - t1) * 1e3
+        # full-size correctness through the factor: ||b - A x|| / ||b|| (A x on the host from the input entries)
+        r = rhs - ch.matvec(xs)
+        solve_res = float(np.linalg.norm(r) / np.linalg.norm(rhs))
 
     if rank == 0:
         peak, peak_how = fp64_peak()
@@ -234,7 +237,7 @@ def main():
                          "kernel_ms": {k: kt[k] for k in ("potrf_ms", "trsm_ms", "gemm_ms")}},
             "factor": {"n": ch.n, "nz": ch.nz, "levels": ch.levels, "flops": flops, "factor_GiB": ch.factor_doubles() * 8 / 2**30,
                        "analyze_s": analyze_s, "assemble_ms": st.assemble_seconds * 1e3, "seconds_best": st.seconds_best,
-                       "residual": res, "solve_ms": solve_ms},
+                       "residual": res, "solve_ms": solve_ms, "solve_rel_residual": solve_res},
         }
         if world > 1:
             line["config"]["parallelism"] = (f"{world} ranks: one subtree per GPU below tree level {world.bit_length() - 1}, top levels "

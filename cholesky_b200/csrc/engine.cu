@@ -386,10 +386,9 @@ static int run_launch(chol_t *c, const Launch &l) {
     case K_BARRIER:
       launch_barrier(c);
       break;
-    case K_ALLREDUCE:
-      launch_barrier(c);
-      allreduce_top<<<148 * 4, 256, 0, c->cur>>>(c->peers, l.count / 2);
-      launch_barrier(c);
+    case K_ALLREDUCE:  // one top panel: shared = its heap index, cfg = mask of contributing ranks
+      allreduce_top<<<148 * 4, 256, 0, c->cur>>>(c->peers, l.begin / 2, l.count / 2, c->S.ld[l.shared] / 2, c->P.sz[l.shared],
+                                                 (unsigned)l.cfg);
       break;
     case K_NOP:
       break;
@@ -463,7 +462,7 @@ int chol_assemble(chol_t *c) {
 // kernels one step launches (the all-reduce is a barrier, the reduction kernel and a barrier)
 static int64_t count_kernels(chol_t *c) {
   int64_t k = 0;
-  for (const Launch &l : c->D.launches) k += l.kind == K_NOP ? 0 : l.kind == K_ALLREDUCE ? 3 : (l.kind == K_GEMM && l.count <= 0) ? 0 : 1;
+  for (const Launch &l : c->D.launches) k += l.kind == K_NOP ? 0 : (l.kind == K_GEMM && l.count <= 0) ? 0 : 1;
   return k;
 }
 
@@ -862,6 +861,19 @@ int chol_solve(chol_t *c, const double *b, double *x) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(x, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* verification helper (host): y = A x with the loaded lower-triangle entries, original dof order */
+int chol_matvec(chol_t *c, const double *x, double *y) {
+  if (!c->loaded) return fail(c, "nothing loaded");
+  const Problem &P = c->P;
+  for (int i = 0; i < P.n; i++) y[i] = 0.0;
+  for (int64_t e = 0; e < P.nz; e++) {
+    const int i = P.ei[e], j = P.ej[e];
+    y[i] += P.ev[e] * x[j];
+    if (i != j) y[j] += P.ev[e] * x[i];
+  }
   return 0;
 }
 

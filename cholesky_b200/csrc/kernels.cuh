@@ -351,18 +351,44 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
 #pragma unroll
       for (int e = 0; e < 2; e++) Cs[(wn0 + j * 8 + 2 * t + e) * kLdC + wm0 + i * 8 + g] = acc[i][j][e];
   asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kConsumers * 32) : "memory");
+  // 16-byte peer stores when every column of the tile starts on a 16-byte boundary (always true for the
+  // in-panel updates; Schur destinations start wherever their cluster starts)
+  const bool vec = (((pr.c_off + row0) | pr.ldc) & 1) == 0;
   for (int j = warp; j < BN; j += Cfg::kConsumers) {
     const int cc = col0 + j;
     if (cc >= pr.N) break;
+    if (vec) {
 #pragma unroll
-    for (int rr = lane; rr < BM; rr += 32) {
-      const int r = row0 + rr;
-      if (r < pr.M && (!pr.tri || r >= cc)) {
+      for (int rr = 2 * lane; rr < BM; rr += 64) {
+        const int r = row0 + rr;
+        const bool ok0 = r < pr.M && (!pr.tri || r >= cc), ok1 = r + 1 < pr.M && (!pr.tri || r + 1 >= cc);
+        if (!ok0 && !ok1) continue;
         const size_t o = r + (size_t)cc * pr.ldc;
-        const double v = C[o] - Cs[j * kLdC + rr];
+        if (ok0 && ok1) {
+          const double2 cv = *reinterpret_cast<const double2 *>(C + o);
+          const double2 v = make_double2(cv.x - Cs[j * kLdC + rr], cv.y - Cs[j * kLdC + rr + 1]);
 #pragma unroll
-        for (int p = 0; p < kMaxPeers; p++)
-          if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
+          for (int p = 0; p < kMaxPeers; p++)
+            if (p < peers.n) *reinterpret_cast<double2 *>(peers.fac[p] + pr.c_off + o) = v;
+        } else {
+          const int q = ok0 ? 0 : 1;
+          const double v = C[o + q] - Cs[j * kLdC + rr + q];
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; p++)
+            if (p < peers.n) peers.fac[p][pr.c_off + o + q] = v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int rr = lane; rr < BM; rr += 32) {
+        const int r = row0 + rr;
+        if (r < pr.M && (!pr.tri || r >= cc)) {
+          const size_t o = r + (size_t)cc * pr.ldc;
+          const double v = C[o] - Cs[j * kLdC + rr];
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; p++)
+            if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
+        }
       }
     }
   }
@@ -570,20 +596,30 @@ __global__ void peer_barrier(Peers peers, unsigned long long epoch) {
 // Sum of all ranks' copies of the top panels: rank r reduces slice r (peer loads over NVLink, fixed
 // summation order, so every rank ends with bit-identical values) and stores the sums into every
 // copy (peer stores).  Bracketed by peer_barrier on both sides.
-__global__ void __launch_bounds__(256) allreduce_top(Peers peers, int64_t n2 /* double2 elements */) {
-  const int64_t lo = n2 * peers.rank / peers.n, hi = n2 * (peers.rank + 1) / peers.n;
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 v[kMaxPeers];
+// One panel per launch (off2 / n2 in double2 units, ld2 = ld / 2, npiv = pivot-block columns): chunks of
+// 4096 double2 go round-robin to the ranks; only the ranks in `mask` hold contributions (the others'
+// copies are still zero), and elements strictly above the pivot block's diagonal are never touched by
+// the factorization, so they are skipped.
+constexpr int kArChunk = 4096;
+__global__ void __launch_bounds__(256) allreduce_top(Peers peers, int64_t off2, int64_t n2, int ld2, int npiv, unsigned mask) {
+  const int64_t nchunks = (n2 + kArChunk - 1) / kArChunk;
+  for (int64_t ch = (int64_t)blockIdx.x * peers.n + peers.rank; ch < nchunks; ch += (int64_t)gridDim.x * peers.n) {
+    for (int64_t i = ch * kArChunk + threadIdx.x; i < min(n2, (ch + 1) * kArChunk); i += blockDim.x) {
+      const int64_t col = i / ld2;
+      const int64_t row = (i - col * ld2) * 2;
+      if (col < npiv && row + 1 < col) continue;
+      const int64_t gi = off2 + i;
+      double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int p = 0; p < kMaxPeers; p++)
-      if (p < peers.n) v[p] = reinterpret_cast<const double2 *>(peers.fac[p])[i];
-    double2 s = v[0];
+      for (int p = 0; p < kMaxPeers; p++)
+        if (p < peers.n && ((mask >> p) & 1u)) {
+          const double2 v = reinterpret_cast<const double2 *>(peers.fac[p])[gi];
+          s.x += v.x, s.y += v.y;
+        }
 #pragma unroll
-    for (int p = 1; p < kMaxPeers; p++)
-      if (p < peers.n) s.x += v[p].x, s.y += v[p].y;
-#pragma unroll
-    for (int p = 0; p < kMaxPeers; p++)
-      if (p < peers.n) reinterpret_cast<double2 *>(peers.fac[p])[i] = s;
+      for (int p = 0; p < kMaxPeers; p++)
+        if (p < peers.n) reinterpret_cast<double2 *>(peers.fac[p])[gi] = s;
+    }
   }
   __threadfence_system();
 }

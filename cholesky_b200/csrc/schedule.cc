@@ -395,9 +395,20 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     B.end_gemm(lvl, PH_UPDATE, top);
 
     // the subtrees are done: sum every rank's copy of the top panels before the top is factored
+    // One reduction per top panel: only the ranks under that separator (and rank 0, which assembled A's
+    // entries) hold contributions, and the strictly upper part of the pivot block is never touched.
     if (world > 1 && lvl == depth) {
       B.depend(0, 1);
-      B.push(Builder::mk(K_ALLREDUCE, lvl, PH_UPDATE, 0, D.top_doubles, 0, 0, 0), 0);
+      B.push(Builder::mk(K_BARRIER, lvl, PH_UPDATE, 0, 0, 0, 0, 0), 0);
+      for (int h = 1; h < (1 << depth); h++) {
+        const int lv = P.level_of(h);
+        unsigned mask = 1u;  // rank 0
+        for (int r = 0; r < world; r++)
+          if ((((1 << depth) + r) >> (depth - lv)) == h) mask |= 1u << r;
+        // begin = panel offset, count = panel doubles, cfg = contributor mask, shared = heap index of the panel
+        B.push(Builder::mk(K_ALLREDUCE, lvl, PH_UPDATE, S.poff[h], S.poff[h + 1] - S.poff[h], 0, (int)mask, h), 0);
+      }
+      B.push(Builder::mk(K_BARRIER, lvl, PH_UPDATE, 0, 0, 0, 0, 0), 0);
     }
   }
   // the step ends on stream 0

@@ -222,6 +222,13 @@ class Cholesky:
         self._ck(self.L.chol_residual(self.h, k, C.c_uint64(seed), C.byref(r)))
         return r.value
 
+    def matvec(self, x):
+        """host check helper: A @ x from the loaded entries (original dof order)"""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        y = np.zeros(self.n, dtype=np.float64)
+        self._ck(self.L.chol_matvec(self.h, _p(x), _p(y)))
+        return y
+
     def solve(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
         x = np.zeros(self.n, dtype=np.float64)

@@ -130,6 +130,7 @@ int chol_residual(chol_t *, int k, uint64_t seed, double *rel);
 
 /* ---- solve (next row f-1).  replaces: mmat.rg:1364-1495, blas.rg:217-290, mnd.c:201-229 */
 int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out */
+int chol_matvec(chol_t *, const double *x, double *y); /* host check helper: y = A x, original dof order */
 int chol_read_vector(const char *path, int n, double *out);
 int chol_write_solution(const char *path, int n, const double *x);
 

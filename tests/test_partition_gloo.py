@@ -82,8 +82,9 @@ def test_partition_covers_single_rank_schedule(world):
     assert 1 in kinds
     # one all-reduce of the top copies per rank, and a barrier after every shared launch
     for r in ranks:
-        assert sum(l["kind"] == "allreduce_top" for l in r["launches"]) == 1
-        assert sum(l["kind"] == "peer_barrier" for l in r["launches"]) == r["stats"]["shared_launches"]
+        # one reduction per shared top panel, bracketed by two barriers; one barrier per broadcast launch
+        assert sum(l["kind"] == "allreduce_top" for l in r["launches"]) == world - 1
+        assert sum(l["kind"] == "peer_barrier" for l in r["launches"]) == r["stats"]["shared_launches"] + 2
         assert r["stats"]["top_doubles"] == ranks[0]["stats"]["top_doubles"] > 0
 
 
