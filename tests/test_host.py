@@ -107,6 +107,61 @@ def test_bad_inputs_are_reported(golden, tmp_path):
         Cholesky().load(g.mtx, g.ord, str(badc)).analyze()
 
 
+def _with_extra_entry(g, tmp_path, extra):
+    """the fixture matrix with one more coordinate line (banner nz bumped)"""
+    lines = open(g.mtx).read().splitlines()
+    n, m, nz = lines[1].split()
+    lines[1] = f"{n} {m} {int(nz) + 1}"
+    p = tmp_path / "extra.mtx"
+    p.write_text("\n".join(lines + [extra]) + "\n")
+    return str(p)
+
+
+def test_entry_between_unrelated_separators_is_dropped_like_the_reference(golden, tmp_path):
+    """no block exists for two separators that are not in an ancestor relation: the reference drops the
+    entry silently (the nz assert is commented out, mmat.rg:1191); pattern and flop count do not change"""
+    g = golden["lapl_25x25"]
+    base = Cholesky().load(g.mtx, g.ord, g.clust).analyze(keep_records=True)
+    perm = base.perm()
+    # permuted rows 0 and 4 belong to leaf separators 1 and 2 (4 dofs each): siblings, unrelated
+    i, j = sorted((int(perm[0]) + 1, int(perm[4]) + 1), reverse=True)
+    m = _with_extra_entry(g, tmp_path, f"{i} {j} -0.5")
+    ch = Cholesky().load(m, g.ord, g.clust).analyze(keep_records=True)
+    o = orc.Oracle(m, g.ord, g.clust)
+    assert ch.nz == base.nz + 1
+    for t in range(ch.levels):
+        np.testing.assert_array_equal(ch.filled(t), base.filled(t))
+        np.testing.assert_array_equal(ch.filled(t), o.filled(t))
+    assert ch.partition_stats()["assembled"] == base.nz     # the extra entry has no destination
+    assert ch.flops() == base.flops() == o.flops()
+
+
+def test_explicit_zero_entry_does_not_fill(golden, tmp_path):
+    """a stored zero is 'empty' to the reference's hash table (mnd.c:178-195) and to fill_block (mmat.rg:591)"""
+    g = golden["lapl_25x25"]
+    base = Cholesky().load(g.mtx, g.ord, g.clust).analyze(keep_records=True)
+    perm = base.perm()
+    i, j = sorted((int(perm[24]) + 1, int(perm[0]) + 1), reverse=True)   # (root dof, leaf dof): a real block
+    m = _with_extra_entry(g, tmp_path, f"{i} {j} 0.0")
+    ch = Cholesky().load(m, g.ord, g.clust).analyze(keep_records=True)
+    for t in range(ch.levels):
+        np.testing.assert_array_equal(ch.filled(t), base.filled(t))
+
+
+def test_matrix_reader_skips_exactly_two_lines(golden, tmp_path):
+    """mnd.c:162-164 skips two lines whatever they hold; a comment line therefore shifts the entries
+    and the last one is lost -- the readers here and in the oracle behave the same way"""
+    g = golden["lapl_9x9"]
+    lines = open(g.mtx).read().splitlines()
+    p = tmp_path / "commented.mtx"
+    p.write_text("\n".join([lines[0], "% a comment"] + lines[1:]) + "\n")
+    ch = Cholesky().load(str(p), g.ord, g.clust).analyze(keep_records=True)
+    o = orc.Oracle(str(p), g.ord, g.clust)
+    assert ch.nz == o.nz == 21          # the banner reader skips comments (mmio.c:189-217) ...
+    for t in range(ch.levels):          # ... but the entry reader does not, and both sides agree on the result
+        np.testing.assert_array_equal(ch.filled(t), o.filled(t))
+
+
 def test_hash_sax_matches_oracle():
     L = _lib.load()
     for k in (0, 1, 24, 3375 * 3374 + 17, 2**40 + 12345):
