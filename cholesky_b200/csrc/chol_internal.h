@@ -133,6 +133,10 @@ struct Schedule {
   // so the large configuration is off by default (CHOL_MIN_TILES_128 re-enables it for experiments).
   int min_tiles_128 = 1 << 30;
   int big_cfg = 1;  // tile configuration of big problems: 1 = 128x128, 2 = 128x64
+  // small fronts: Schur problems with M, N <= small_mn and total K <= small_k run as one warp per 32x32
+  // tile (cfg 3, gemm_small_warp): no shared memory, no barriers (CHOL_SMALL_FRONT=0: off)
+  bool small_front = true;
+  int small_mn = 96, small_k = 512;
   // multi-GPU partition (world = 2^depth ranks)
   int rank = 0, world = 1, depth = 0;
   bool split_phases = false;  // true: fused_dpotrf and fused_dtrsm as separate launch sequences (piecewise API)

@@ -368,7 +368,10 @@ static int run_launch(chol_t *c, const Launch &l) {
       break;
     case K_GEMM:
       if (l.count <= 0) break;
-      if (l.cfg == 2)
+      if (l.cfg == 3)
+        gemm_small_warp<<<(unsigned)((l.count + kSmallWarps - 1) / kSmallWarps), kSmallWarps * 32, 0, c->cur>>>(
+            c->d_probs, c->d_contribs, c->d_tiles + l.begin, l.count, c->d_fac);
+      else if (l.cfg == 2)
         launch_gemm_ws<128, 64, 16, 32, 32, 4, 2>(c, l);
       else if (l.cfg == 1 && c->gemm_ws)
         launch_gemm_ws<128, 128, 16, 32, 32, 4, 1>(c, l);

@@ -396,6 +396,67 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
 }
 
 // ---------------------------------------------------------------------------------------------
+// gemm_small_warp: the same grouped update for the small fronts at the bottom of the tree.  One warp
+// per 32x32 destination tile, register-blocked (16 DMMA accumulator blocks), operands read straight
+// from global memory in the DMMA fragment pattern (eight consecutive rows per column: 64-byte runs,
+// L2-resident), no shared memory and no barriers, so thousands of tiny problems run per launch without
+// per-CTA pipeline set-up.  Contributors are still accumulated in their fixed order.
+constexpr int kSmallWarps = 4;
+__global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmProblem *__restrict__ probs,
+                                                                    const GemmContrib *__restrict__ contribs,
+                                                                    const TileRef *__restrict__ tiles, int64_t ntiles,
+                                                                    double *__restrict__ fac) {
+  const int64_t ti = (int64_t)blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
+  if (ti >= ntiles) return;
+  const TileRef tile = tiles[ti];
+  const GemmProblem pr = probs[tile.prob];
+  const int row0 = tile.tr * 32, col0 = tile.tc * 32;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  bool rok[4], cok[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) rok[i] = row0 + i * 8 + g < pr.M, cok[i] = col0 + i * 8 + g < pr.N;
+  for (int c = 0; c < pr.contrib_count; c++) {
+    const GemmContrib cb = contribs[pr.contrib_begin + c];
+    const double *__restrict__ A = fac + cb.a_off + row0 + g;
+    const double *__restrict__ Bp = fac + cb.b_off + col0 + g;
+    const int K = cb.K;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const bool kok = k0 + t < K;
+      const size_t ka = (size_t)(k0 + t) * cb.lda, kb = (size_t)(k0 + t) * cb.ldb;
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = (kok && rok[i]) ? A[ka + i * 8] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = (kok && cok[j]) ? Bp[kb + j * 8] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  double *__restrict__ C = fac + pr.c_off;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = row0 + i * 8 + g;
+    if (r >= pr.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + j * 8 + 2 * t + e;
+        if (cc < pr.N && (!pr.tri || r >= cc)) C[r + (size_t)cc * pr.ldc] -= acc[i][j][e];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
 // Pivot tile in shared memory (row stride 65: conflict-free), blocked by 16 columns.  Inside a block:

@@ -81,8 +81,8 @@ struct Builder {
     mode = m;
   }
   bool is_big(const GemmProblem &g) const { return g.M >= D.big_m && g.N >= D.big_n; }
-  static int cfg_bm(int cfg) { return cfg == 0 ? 64 : 128; }
-  static int cfg_bn(int cfg) { return cfg == 1 ? 128 : 64; }
+  static int cfg_bm(int cfg) { return cfg == 3 ? 32 : cfg == 0 ? 64 : 128; }
+  static int cfg_bn(int cfg) { return cfg == 3 ? 32 : cfg == 1 ? 128 : 64; }
   static int64_t ntiles(const GemmProblem &g, int cfg) {
     const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
     int64_t tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
@@ -176,10 +176,19 @@ struct Builder {
       if (is_big(D.probs[pd.prob])) n128 += ntiles(D.probs[pd.prob], D.big_cfg);
     int64_t share = (top && D.world > 1) ? D.world : 1;
     bool use128 = n128 >= (int64_t)D.min_tiles_128 * share;
-    std::vector<Pending> l128, l64;
-    for (const Pending &pd : pend) (use128 && is_big(D.probs[pd.prob]) ? l128 : l64).push_back(pd);
+    // small fronts (bottom of the tree): one warp per 32x32 tile, operands straight from global memory
+    const bool small_ok = D.small_front && mode == 0 && !(top && D.world > 1);
+    std::vector<Pending> l128, l64, lsmall;
+    for (const Pending &pd : pend) {
+      const GemmProblem &g = D.probs[pd.prob];
+      int ksum = 0;
+      for (int c = 0; c < g.contrib_count; c++) ksum += D.contribs[g.contrib_begin + c].K;
+      if (small_ok && g.M <= D.small_mn && g.N <= D.small_mn && ksum <= D.small_k) lsmall.push_back(pd);
+      else (use128 && is_big(g) ? l128 : l64).push_back(pd);
+    }
     emit(level, phase, D.big_cfg, l128, top);
     emit(level, phase, 0, l64, top);
+    emit(level, phase, 3, lsmall, top);
   }
 };
 
@@ -209,6 +218,9 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);        // tuning knob
   if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   if (const char *e = getenv("CHOL_LOOKAHEAD")) D.lookahead = atoi(e) != 0;
+  if (const char *e = getenv("CHOL_SMALL_FRONT")) D.small_front = atoi(e) != 0;
+  if (const char *e = getenv("CHOL_SMALL_MN")) D.small_mn = atoi(e);
+  if (const char *e = getenv("CHOL_SMALL_K")) D.small_k = atoi(e);
   if (const char *e = getenv("CHOL_NBO")) D.nbo = std::max(64, atoi(e) / 64 * 64);  // tuning knob: block-column width
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
