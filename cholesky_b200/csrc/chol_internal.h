@@ -136,7 +136,7 @@ struct Schedule {
   // small fronts: Schur problems with M, N <= small_mn and total K <= small_k run as one warp per 32x32
   // tile (cfg 3, gemm_small_warp): no shared memory, no barriers (CHOL_SMALL_FRONT=0: off)
   bool small_front = true;
-  int small_mn = 96, small_k = 512;
+  int small_mn = 64, small_k = 256;  // (48..96, 128..512 measured within noise of each other on 128^3)
   // multi-GPU partition (world = 2^depth ranks)
   int rank = 0, world = 1, depth = 0;
   bool split_phases = false;  // true: fused_dpotrf and fused_dtrsm as separate launch sequences (piecewise API)

@@ -59,8 +59,7 @@ struct chol {
   unsigned long long epoch = 0;
   bool peers_ready = false;
   int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
-                            // 128^3), 2 = same with 4 stages / 3 CTAs per SM, 0 = cp.async kernel
-  int gemm128_variant = 0;  // CHOL_GEMM128: 0 = 8 warps of 64x32, 1 = 16 warps of 32x32, 2 = 16 warps, BK 8
+                            // 128^3), 0 = the earlier cp.async kernel
   std::vector<void *> ipc_opened;
 };
 
@@ -86,7 +85,6 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   if (!out) return -1;
   chol_t *c = new chol();
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
-  if (const char *e = getenv("CHOL_GEMM128")) c->gemm128_variant = atoi(e);
   if (const char *e = getenv("CHOL_GEMM_WS")) c->gemm_ws = atoi(e);
   *out = c;
   return 0;
@@ -373,16 +371,10 @@ static int run_launch(chol_t *c, const Launch &l) {
             c->d_probs, c->d_contribs, c->d_tiles + l.begin, l.count, c->d_fac);
       else if (l.cfg == 2)
         launch_gemm_ws<128, 64, 16, 32, 32, 4, 2>(c, l);
-      else if (l.cfg == 1 && c->gemm_ws)
+      else if (l.cfg == 1)
         launch_gemm_ws<128, 128, 16, 32, 32, 4, 1>(c, l);
-      else if (l.cfg == 1) {
-        if (c->gemm128_variant == 1) launch_gemm<128, 128, 16, 32, 32, 4>(c, l);
-        else if (c->gemm128_variant == 2) launch_gemm<128, 128, 8, 32, 32, 6>(c, l);
-        else launch_gemm<128, 128, 16, 64, 32, 4>(c, l);
-      } else if (c->gemm_ws == 1)
+      else if (c->gemm_ws)
         launch_gemm_ws<64, 64, 16, 32, 32, 3, 4>(c, l);
-      else if (c->gemm_ws == 2)
-        launch_gemm_ws<64, 64, 16, 32, 32, 4, 3>(c, l);
       else
         launch_gemm<64, 64, 16, 32, 32, 3>(c, l);
       break;
