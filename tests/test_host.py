@@ -84,6 +84,33 @@ def test_generated_nd_files_roundtrip_and_match_oracle(grid, tmp_path):
     assert oc.factor_nnz() == ch.nz
 
 
+def test_random_grids_symbolic_parity(tmp_path):
+    """ragged shapes: 40 seeded random grids / stencils / tree depths, pattern bit for bit against the oracle"""
+    rng = np.random.default_rng(7)
+    done = 0
+    while done < 40:
+        three_d = rng.random() < 0.6
+        nx, ny = int(rng.integers(3, 14)), int(rng.integers(3, 14))
+        nz = int(rng.integers(2, 10)) if three_d else 1
+        st = (7 if rng.random() < 0.6 else 27) if three_d else 5
+        lv = int(rng.integers(1, 5))
+        try:
+            ch = Cholesky().generate(nx, ny, nz, st, lv)
+        except CholeskyError:          # too many levels for this grid: an empty separator is refused
+            continue
+        m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+        ch.write_inputs(m, o, c)
+        ch.analyze(keep_records=True)
+        oc = orc.Oracle(m, o, c)
+        np.testing.assert_array_equal(ch.perm(), oc.perm())
+        for t in range(ch.levels):
+            np.testing.assert_array_equal(ch.filled(t), oc.filled(t), err_msg=str((nx, ny, nz, st, lv, t)))
+        assert ch.call_counts() == oc.call_counts() and ch.flops() == oc.flops()
+        oc.assemble()
+        assert oc.factor_nnz() == ch.nz, (nx, ny, nz, st, lv)      # true vertex separators: nothing dropped
+        done += 1
+
+
 def test_levels_rule_matches_utils_py():
     import math
     for dims, st in [((512, 512, 1), 5), ((64, 64, 64), 7)]:
