@@ -19,6 +19,8 @@
 
 using namespace chb;
 
+constexpr int kMaxDevices = 16;
+
 
 struct SolveDev;
 struct chol {
@@ -321,11 +323,12 @@ static int do_assemble(chol_t *c) {
 template <int BM, int BN, int BK, int WM, int WN, int ST>
 static void launch_gemm(chol_t *c, const Launch &l) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, ST>;
-  static bool attr[2] = {false, false};  // one device per process
-  if (!attr[(l.shared == 1) ? 1 : 0]) {
+  static bool attr[kMaxDevices][2] = {};  // the opt-in shared-memory size is a per-device function attribute
+  bool &done = attr[c->device % kMaxDevices][(l.shared == 1) ? 1 : 0];
+  if (!done) {
     if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     else cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    attr[(l.shared == 1) ? 1 : 0] = true;
+    done = true;
   }
   if (l.shared == 1)
     gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
@@ -337,11 +340,12 @@ static void launch_gemm(chol_t *c, const Launch &l) {
 template <int BM, int BN, int BK, int WM, int WN, int ST, int MINB>
 static void launch_gemm_ws(chol_t *c, const Launch &l) {
   using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, ST>;
-  static bool attr[2] = {false, false};
-  if (!attr[(l.shared == 1) ? 1 : 0]) {
+  static bool attr[kMaxDevices][2] = {};
+  bool &done = attr[c->device % kMaxDevices][(l.shared == 1) ? 1 : 0];
+  if (!done) {
     if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     else cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    attr[(l.shared == 1) ? 1 : 0] = true;
+    done = true;
   }
   if (l.shared == 1)
     gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
@@ -721,7 +725,8 @@ int chol_write_factor(chol_t *c, const char *path, int full) {
   MM_typecode tc;
   memcpy(tc, c->P.typecode, 4);
   mm_write_banner(f, tc);
-  mm_write_mtx_crd_size(f, c->P.n, c->P.ncols, (int)nnz);
+  if (nnz <= 0x7fffffff) mm_write_mtx_crd_size(f, c->P.n, c->P.ncols, (int)nnz);
+  else fprintf(f, "%d %d %lld\n", c->P.n, c->P.ncols, (long long)nnz);  // mmio's int count overflows (128^3: 3.4e9 entries)
   visit(c, [&](int i, int j, double v) { fprintf(f, full ? "%d %d %.17g\n" : "%d %d %0.8g\n", i + 1, j + 1, v); });
   fclose(f);
   return 0;

@@ -1,15 +1,18 @@
-// sm_100a kernels of the numeric factorization.  Three grouped kernels execute the whole level
+// sm_100a kernels of the numeric factorization.  A handful of grouped kernels execute the whole level
 // schedule (see schedule.cc); one scatter kernel assembles A; two small kernels carry the multi-GPU
 // exchange over NVLink peer memory.
 //
-//   gemm_grouped   C -= sum_c A_c B_c^T on FP64 tensor cores (mma.sync DMMA m8n8k4), operands
-//                  staged through shared memory by a multi-stage cp.async pipeline, one CTA per
+//   gemm_grouped_ws  C -= sum_c A_c B_c^T on FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4),
+//                  warp-specialised: a producer warp stages operand tiles with the TMA bulk-copy engine
+//                  (cp.async.bulk + mbarrier expect_tx), consumer warps issue the MMAs; one CTA per
 //                  destination tile, contributors accumulated in registers in a fixed order
 //                  (atomic-free, deterministic), lower-triangle masking for SYRK destinations.
 //                  SHARED variant: the tile is also stored into every peer's copy of the factor
-//                  (P2P stores), fusing the update with its broadcast.
+//                  (coalesced P2P stores), fusing the update with its broadcast.
 //                  Replaces cblas_dgemm / cblas_dsyrk as called at blas.rg:139-142, 187-189.
-//   potrf_tile     Cholesky of one NB x NB pivot tile, one row per thread in registers
+//   gemm_grouped   the earlier cp.async version of the same kernel (CHOL_GEMM_WS=0).
+//   gemm_small_warp  the same update for small fronts: one warp per 32x32 tile, no shared memory.
+//   potrf_tile     Cholesky of one NB x NB pivot tile in shared memory, blocked by 16 columns
 //                  (LAPACKE_dpotrf, blas.rg:71).
 //   trsm_tile      one 128-row slab times L^-T by forward substitution, one row per thread
 //                  (cblas_dtrsm Right/Lower/Trans/NonUnit, blas.rg:99-100).
