@@ -60,6 +60,7 @@ struct chol {
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  int potrf_w = 1;          // CHOL_POTRF_W: 1 = single-warp column steps (potrf_tile_w), 0 = 64-thread version
   int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
                             // 128^3), 0 = the earlier cp.async kernel
   std::vector<void *> ipc_opened;
@@ -88,6 +89,7 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   chol_t *c = new chol();
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
   if (const char *e = getenv("CHOL_GEMM_WS")) c->gemm_ws = atoi(e);
+  if (const char *e = getenv("CHOL_POTRF_W")) c->potrf_w = atoi(e);
   *out = c;
   return 0;
 }
@@ -363,7 +365,8 @@ static void launch_barrier(chol_t *c) {
 static int run_launch(chol_t *c, const Launch &l) {
   switch (l.kind) {
     case K_POTRF:
-      potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      if (c->potrf_w) potrf_tile_w<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      else potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
       trsm_tile<<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);

@@ -549,6 +549,93 @@ __global__ void __launch_bounds__(kPotrfThreads) potrf_tile(const PotrfDesc *__r
   }
 }
 
+// potrf_tile_w: same tile, but the column steps are done by ONE warp (two rows per lane) so that the 64
+// dependent steps synchronise with __syncwarp and a shuffle instead of block barriers and a round trip
+// through shared memory; every lane computes the pivot's 1/sqrt itself.  Blocks of 8 columns keep the
+// in-block dot products short; the rank-8 trailing update uses all 256 threads.
+constexpr int kPB2 = 8;
+__global__ void __launch_bounds__(kPotrfThreads) potrf_tile_w(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+                                                              int *__restrict__ info) {
+  __shared__ double T[kNB][kNB + 1];
+  const PotrfDesc d = descs[blockIdx.x];
+  double *__restrict__ A = fac + d.off;
+  const int nb = d.nb, tid = threadIdx.x, lane = tid & 31;
+  {
+    const int i = tid & (kNB - 1), cg = tid / kNB;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int c = cg * 16 + h * 8 + u;
+        v[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) T[i][cg * 16 + h * 8 + u] = v[u];
+    }
+  }
+  __syncthreads();
+  for (int kb = 0; kb < nb; kb += kPB2) {
+    const int kend = min(kb + kPB2, nb);
+    if (tid < 32) {
+      const int r0 = lane, r1 = lane + 32;
+      for (int k = kb; k < kend; k++) {
+        double s0 = 0.0, s1 = 0.0;
+        if (r0 >= k && r0 < nb) s0 = T[r0][k];
+        if (r1 >= k && r1 < nb) s1 = T[r1][k];
+        for (int j = kb; j < k; j++) {
+          const double b = T[k][j];
+          s0 -= T[r0][j] * b;  // rows above the diagonal or beyond nb compute garbage that is never stored
+          s1 -= T[r1][j] * b;
+        }
+        double sk = __shfl_sync(0xffffffffu, k < 32 ? s0 : s1, k & 31);
+        if (!(sk > 0.0)) {
+          if (lane == 0) atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+          sk = 1.0;
+        }
+        // 1/sqrt from the single-precision seed and two Newton steps in double (error ~2 ulp); the
+        // library routine's longer dependent chain sits on the critical path of all 64 columns
+        double r;
+        if (sk > 1e-30 && sk < 1e30) {
+          r = (double)rsqrtf((float)sk);
+          const double hs = 0.5 * sk;
+          r = r * (1.5 - hs * r * r);
+          r = r * (1.5 - hs * r * r);
+        } else
+          r = rsqrt(sk);
+        if (r0 == k || r1 == k) T[k][k] = sk * r;
+        if (r0 > k && r0 < nb) T[r0][k] = s0 * r;
+        if (r1 > k && r1 < nb) T[r1][k] = s1 * r;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const int rem = nb - kend;
+    if (rem > 0) {
+      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
+        const int i = kend + idx % rem, j = kend + idx / rem;
+        if (i < j) continue;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (int k = kb; k < kend; k += 2) {
+          s0 += T[i][k] * T[j][k];
+          if (k + 1 < kend) s1 += T[i][k + 1] * T[j][k + 1];
+        }
+        T[i][j] -= s0 + s1;
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const int i = tid & (kNB - 1), cg = tid / kNB;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int c = cg * 16 + u;
+      if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = T[i][c];
+    }
+  }
+}
+
 // 128-row slab per CTA, one row per thread.  The slab (k-major, so a warp reads consecutive words) and
 // L^T live in shared memory; columns are solved eight at a time with eight independent FMA chains, the
 // eight multipliers of one k come as four broadcast vector loads.  Loops are deliberately not fully
