@@ -1,6 +1,7 @@
 // Internal data model of the engine: problem -> symbolic structure -> device schedule.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -146,7 +147,22 @@ struct Schedule {
   double shared_min_flops = 2e9;   // top-level GEMM launches at least this large are split across ranks
 };
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err);
+// only_heap != 0: the launches of that one separator alone (no assembly map) -- the stepwise debug trace
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err,
+                   int only_heap = 0);
+
+// ----------------------------------------------------------------------------- debug trace (`-d`)
+// One fused task of the reference's level loop (mmat.rg:1240-1343) and the snapshot it is followed by.
+struct DebugStep {
+  int op;  // 0 POTRF, 1 TRSM, 2 GEMM (fused_dsyrk / fused_dgemm)
+  int lvl;
+  int hs, hp, hg;    // heap indices: eliminated separator, parent-side and grandparent-side ancestors
+  std::string name;  // gen_filename (mmat.rg:149-172) without directory and extension
+};
+std::vector<DebugStep> debug_steps(const Problem &P);
+// the whole `-d` log of one factorization: Block / Cluster / Fill lines of the symbolic phase and the
+// POTRF / TRSM / GEMM lines of the level loop, in program order (needs Symbolic::records)
+int write_debug_log(const Problem &P, const Symbolic &S, FILE *f, std::string &err);
 
 uint64_t mix64(uint64_t x);
 uint64_t filled_hash(const FilledRec &r);

@@ -1,6 +1,6 @@
 // `cholesky` command line: the reference's flags (mmat.rg:1072-1093) over the C ABI.
 //   -i matrix.mtx -s separators.txt -c clusters.txt [-b rhs.mtx -o solution] [-m factor.mtx]
-//   [-p permuted.mtx] [--iterations N] [--gpu D]
+//   [-p permuted.mtx] [-d debug_dir] [--iterations N] [--gpu D]
 // Progress lines follow the reference's stdout (mmat.rg:1095-1121, 1228, 1357).
 #include <cstdio>
 #include <cstdlib>
@@ -10,7 +10,7 @@
 #include "../../include/cholesky.h"
 
 int main(int argc, char **argv) {
-  const char *mat = "", *sep = "", *clu = "", *bfile = "", *sol = "", *fac = "", *perm = "";
+  const char *mat = "", *sep = "", *clu = "", *bfile = "", *sol = "", *fac = "", *perm = "", *dbg = "";
   int iterations = 1, gpu = 0;
   for (int i = 0; i + 1 < argc; i++) {
     if (!strcmp(argv[i], "-i")) mat = argv[i + 1];
@@ -20,6 +20,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "-p")) perm = argv[i + 1];
     else if (!strcmp(argv[i], "-o")) sol = argv[i + 1];
     else if (!strcmp(argv[i], "-b")) bfile = argv[i + 1];
+    else if (!strcmp(argv[i], "-d")) dbg = argv[i + 1];  // debug_path, debug = true (mmat.rg:1086-1090)
     else if (!strcmp(argv[i], "--iterations")) iterations = atoi(argv[i + 1]);
     else if (!strcmp(argv[i], "--gpu")) gpu = atoi(argv[i + 1]);
   }
@@ -31,7 +32,7 @@ int main(int argc, char **argv) {
     return 1;
   }
   printf("M: %d N: %d nz: %lld\n", chol_n(c), chol_n(c), (long long)chol_nz(c));
-  if (chol_analyze(c, 0)) {
+  if (chol_analyze(c, *dbg ? 1 : 0)) {
     printf("%s\n", chol_last_error(c));
     return 1;
   }
@@ -45,11 +46,20 @@ int main(int argc, char **argv) {
     printf("saving matrix to: %s\n\n", perm);
   }
   chol_stats_t st;
-  if (chol_factor(c, iterations, 0, &st)) {
+  if (*dbg) {
+    // the debug run: log lines on stdout (redirect them to the file verify.debug_factor reads), one
+    // snapshot per fused task under the debug path, then the regular outputs from the same factor
+    if (chol_write_debug_log(c, nullptr) || chol_factor_debug(c, dbg, 0, 1)) {
+      printf("%s\n", chol_last_error(c));
+      return 1;
+    }
+    st.seconds_best = 0, st.flops = 0, st.kernel_launches = 0;
+  } else if (chol_factor(c, iterations, 0, &st)) {
     printf("%s\n", chol_last_error(c));
     return 1;
   }
-  printf("Done factoring: %.6f s (best of %d), %.3f GFLOP/s, %lld kernels per iteration\n", st.seconds_best, iterations,
+  if (!*dbg)
+    printf("Done factoring: %.6f s (best of %d), %.3f GFLOP/s, %lld kernels per iteration\n", st.seconds_best, iterations,
          st.flops / st.seconds_best * 1e-9, (long long)st.kernel_launches);
   if (*fac) {
     printf("saving matrix to: %s\n\n", fac);

@@ -719,8 +719,7 @@ int chol_get_factor_dense(chol_t *c, double *out) {
   visit(c, [&](int i, int j, double v) { out[(size_t)i * n + j] = v; });
   return 0;
 }
-int chol_write_factor(chol_t *c, const char *path, int full) {
-  if (fetch_factor(c)) return -1;
+static int write_factor_file(chol_t *c, const char *path, int full) {
   FILE *f = fopen(path, "w");
   if (!f) return fail(c, std::string("cannot write ") + path);
   int64_t nnz = 0;
@@ -731,7 +730,104 @@ int chol_write_factor(chol_t *c, const char *path, int full) {
   if (nnz <= 0x7fffffff) mm_write_mtx_crd_size(f, c->P.n, c->P.ncols, (int)nnz);
   else fprintf(f, "%d %d %lld\n", c->P.n, c->P.ncols, (long long)nnz);  // mmio's int count overflows (128^3: 3.4e9 entries)
   visit(c, [&](int i, int j, double v) { fprintf(f, full ? "%d %d %.17g\n" : "%d %d %0.8g\n", i + 1, j + 1, v); });
+  const bool bad = ferror(f) != 0;
+  if (fclose(f) != 0 || bad) return fail(c, std::string("write error on ") + path);
+  return 0;
+}
+int chol_write_factor(chol_t *c, const char *path, int full) {
+  if (fetch_factor(c)) return -1;
+  return write_factor_file(c, path, full);
+}
+
+// ------------------------------------------------------------------------------ debug trace (`-d`)
+int chol_write_debug_log(chol_t *c, const char *path) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  FILE *f = path ? fopen(path, "w") : stdout;
+  if (!f) return fail(c, std::string("cannot write ") + path);
+  int rc = write_debug_log(c->P, c->S, f, c->err);
+  if (path) fclose(f);
+  else fflush(f);
+  return rc;
+}
+
+// the human-readable companion of a snapshot (write_blocks, mmat.rg:185-217): every block, dense, "%0.2f"
+static int write_blocks_txt(chol_t *c, const char *path, const DebugStep &st) {
+  const Problem &P = c->P;
+  const Symbolic &S = c->S;
+  FILE *f = fopen(path, "w");
+  if (!f) return fail(c, std::string("cannot write ") + path);
+  const int ls = P.label_of(st.hs), lp = st.hp ? P.label_of(st.hp) : 0, lg = st.hg ? P.label_of(st.hg) : 0;
+  if (st.op == 0) fprintf(f, "Level: %d POTRF A=(%d, %d)\n", st.lvl, ls, ls);
+  else if (st.op == 1) fprintf(f, "Level: %d TRSM A=(%d, %d) B=(%d, %d)\n", st.lvl, ls, ls, lp, ls);
+  else fprintf(f, "Level: %d GEMM A=(%d, %d) B=(%d, %d) C=(%d, %d)\n", st.lvl, lg, ls, lp, ls, lg, lp);
+  std::vector<double> blk;
+  for (int lr = 1; lr <= P.N; lr++)
+    for (int lc = 1; lc <= lr; lc++) {
+      const int hr = P.heap_of(lr), hc = P.heap_of(lc), d = P.level_of(hc) - P.level_of(hr);
+      if (d < 0 || (hc >> d) != hr) continue;
+      const int m = P.sz[hr], n = P.sz[hc];
+      if (m == 0 || n == 0) continue;
+      fprintf(f, "Color: %d %d size: %dx%d bounds.lo: %d %d bounds.hi: %d %d vol: %lld\n", lr, lc, m, n, P.start[hr], P.start[hc],
+              P.start[hr] + m - 1, P.start[hc] + n - 1, (long long)m * n);
+      blk.assign((size_t)m * n, 0.0);
+      const double *pan = c->h_fac.data() + S.poff[hc];
+      for (int64_t s = S.seg_ptr[hc]; s < S.seg_ptr[hc + 1]; s++) {
+        const Seg &sg = S.segs[s];
+        if (sg.anc != hr) continue;
+        for (int r = 0; r < sg.hi - sg.lo; r++)
+          for (int col = 0; col < n; col++) blk[(size_t)(sg.lo + r) * n + col] = pan[sg.off + r + (size_t)col * S.ld[hc]];
+      }
+      for (int i = 0; i < m; i++) {
+        for (int j = 0; j < n; j++) {
+          const double v = blk[(size_t)i * n + j];
+          fprintf(f, v < 0 ? "%0.2f, " : " %0.2f, ", v);
+        }
+        fprintf(f, "\n");
+      }
+    }
   fclose(f);
+  return 0;
+}
+
+/* The level loop one fused task group at a time (mmat.rg:1240-1343 with debug = true): the schedule
+ * compiler is asked for the launches of ONE separator and ONE phase, the GPU runs them, and the factor
+ * as it then stands is written under every file name the reference would write at that point.
+ * fused_dtrsm of one separator runs for all its ancestors at once, and so do its Schur updates, so the
+ * snapshots of one such group are identical; verify.debug_factor compares only the block an operation
+ * wrote (verify.py:98-124), which is final within its group. */
+int chol_factor_debug(chol_t *c, const char *dir, int full_precision, int with_txt) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  if (c->world > 1) return fail(c, "the debug trace runs on a single-GPU handle");
+  if (c->P.n > 20000) return fail(c, "the debug trace writes the whole factor after every fused task: small problems only (n <= 20000)");
+  if (ensure_device(c)) return -1;
+  CK(cudaStreamSynchronize(c->stream));
+  if (do_assemble(c)) return -1;
+  Schedule saved = std::move(c->D);
+  int rc = 0;
+  const std::vector<DebugStep> steps = debug_steps(c->P);
+  for (size_t i = 0; i < steps.size() && !rc;) {
+    size_t j = i;
+    while (j < steps.size() && steps[j].op == steps[i].op && steps[j].hs == steps[i].hs) j++;
+    const int phase = steps[i].op == 0 ? PH_POTRF : steps[i].op == 1 ? PH_TRSM : PH_UPDATE;
+    if (build_schedule(c->P, c->S, c->D, 0, 1, true, c->err, steps[i].hs)) rc = -1;
+    if (!rc) rc = upload_schedule(c);
+    if (!rc) rc = run_levels(c, steps[i].lvl, steps[i].lvl, phase, false);
+    c->h_fac_valid = false;
+    if (!rc) rc = fetch_factor(c);
+    for (size_t k = i; k < j && !rc; k++) {
+      const std::string base = std::string(dir) + "/" + steps[k].name;
+      rc = write_factor_file(c, (base + ".mtx").c_str(), full_precision);
+      if (!rc && with_txt) rc = write_blocks_txt(c, (base + ".txt").c_str(), steps[k]);
+    }
+    i = j;
+  }
+  cudaStreamSynchronize(c->stream);
+  c->D = std::move(saved);
+  if (upload_schedule(c)) return -100;
+  if (rc) return rc;
+  int info = 0;
+  if (fetch_info(c, &info)) return -1;
+  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
   return 0;
 }
 

@@ -205,7 +205,7 @@ struct Pair {  // one (A cluster, B cluster) contribution of separator hs
 
 }  // namespace
 
-int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err) {
+int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err, int only_heap) {
   D = Schedule();
   D.rank = rank, D.world = world;
   D.split_phases = split_phases;
@@ -213,6 +213,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   while ((1 << depth) < world) depth++;
   if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
   if (depth >= P.levels) return err = "more ranks than subtrees", -1;
+  if (only_heap && (world != 1 || only_heap < 1 || only_heap > P.N)) return err = "a single-separator schedule needs a single-GPU handle and a valid separator", -1;
   D.depth = depth;
   if (const char *e = getenv("CHOL_BIG_CFG")) D.big_cfg = atoi(e);                    // tuning knob: 1 = 128x128, 2 = 128x64
   if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);        // tuning knob
@@ -248,7 +249,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
 
   // ---- assembly map (fill_block, mmat.rg:529-633, as a scatter).  With several ranks an entry is
   // assembled by the owner of its column separator; top entries by rank 0 only (the copies are summed).
-  {
+  if (!only_heap) {
     std::vector<int> iperm(P.n), rowheap(P.n);
     for (int p = 0; p < P.n; p++) iperm[P.perm[p]] = p;
     for (int h = 1; h <= N; h++)
@@ -272,8 +273,10 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   std::vector<Pair> pairs;
   for (int lvl = L - 1; lvl >= 0; lvl--) {
     const bool top = lvl < depth;
+    if (only_heap && P.level_of(only_heap) != lvl) continue;
     // separators of this level this rank works on
     int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    if (only_heap) h0 = only_heap, h1 = only_heap + 1;  // debug trace: one fused task group at a time
     if (!top && world > 1) {
       h0 = ((1 << depth) + rank) << (lvl - depth);
       h1 = h0 + (1 << (lvl - depth));

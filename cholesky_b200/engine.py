@@ -217,6 +217,15 @@ class Cholesky:
     def write_factor(self, path, full_precision=False):
         self._ck(self.L.chol_write_factor(self.h, path.encode(), 1 if full_precision else 0))
 
+    # ---- debug trace, the `-d` path (mmat.rg:1086-1090; verify.py:216-275 replays it)
+    def write_debug_log(self, path=None):
+        """the log lines of a debug run (host only; needs analyze(keep_records=True)); None: stdout"""
+        self._ck(self.L.chol_write_debug_log(self.h, path.encode() if path else None))
+
+    def factor_debug(self, directory, full_precision=False, with_txt=False):
+        """level loop one fused task group at a time on the GPU, one snapshot file per reference task"""
+        self._ck(self.L.chol_factor_debug(self.h, directory.encode(), 1 if full_precision else 0, 1 if with_txt else 0))
+
     def residual(self, k=16, seed=1):
         r = C.c_double()
         self._ck(self.L.chol_residual(self.h, k, C.c_uint64(seed), C.byref(r)))

@@ -128,6 +128,16 @@ int chol_write_factor(chol_t *, const char *path, int full_precision);     /* "%
 /* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F, W = k Rademacher columns (seeded) */
 int chol_residual(chol_t *, int k, uint64_t seed, double *rel);
 
+/* ---- debug trace (next row f-3).  replaces: the `-d <dir>` path of mmat.rg (1086-1090): the log lines
+ * printed with debug = true (mmat.rg:331, 352, 396, 432, 1010; blas.rg:308, 340, 405, 422, 490) and the
+ * per-task snapshots of write_blocks (mmat.rg:149-218), i.e. the inputs of verify.debug_factor
+ * (verify.py:216-275).  Analyze with keep_records first.  The log is host-only (path NULL: stdout).
+ * chol_factor_debug assembles, then runs the level loop one fused task group at a time on the GPU and
+ * writes <dir>/{potrf,trsm,gemm}_lvl<L>_a..[_b..][_c..].mtx after each (and the "%0.2f" block dump
+ * .txt when with_txt != 0); it leaves the complete factor in the handle. */
+int chol_write_debug_log(chol_t *, const char *log_path);
+int chol_factor_debug(chol_t *, const char *dir, int full_precision, int with_txt);
+
 /* ---- solve (next row f-1).  replaces: mmat.rg:1364-1495, blas.rg:217-290, mnd.c:201-229 */
 int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out */
 int chol_matvec(chol_t *, const double *x, double *y); /* host check helper: y = A x, original dof order */

@@ -821,7 +821,23 @@ typedef struct {
   int dry, lvl, t;
   double fl[4];
   int64_t calls[4];
+  FILE *log; /* debug trace (`-d`): the fused tasks print one line per BLAS call, blas.rg:308,340,405,422,490 */
 } ctx_t;
+
+static void rec_to_filled(orc_t *o, int t, const rec_t *r, orc_filled_t *f);
+/* "'X': (sx, sy, z), 'X_Lo': (..), 'X_Hi': (..), '<size>X': (..), " -- one operand of a debug line */
+static void log_operand(ctx_t *c, const char *name, const char *size_key, const rec_t *r) {
+  orc_filled_t f;
+  rec_to_filled(c->o, c->t, r, &f);
+  fprintf(c->log, "'%s': (%lld, %lld, %lld), '%s_Lo': (%lld, %lld), '%s_Hi': (%lld, %lld), '%s%s': (%lld, %lld), ", name,
+          (long long)f.sep_x, (long long)f.sep_y, (long long)f.cluster, name, (long long)f.lo_x, (long long)f.lo_y, name,
+          (long long)f.hi_x, (long long)f.hi_y, size_key, name, (long long)(f.hi_x - f.lo_x + 1), (long long)(f.hi_y - f.lo_y + 1));
+}
+static void log_tail(ctx_t *c, const rec_t *blockrec) {
+  orc_filled_t f;
+  rec_to_filled(c->o, c->t, blockrec, &f);
+  fprintf(c->log, "'Block': (%lld, %lld), 'Level': %d, 'Interval': %d}\n", (long long)f.sep_x, (long long)f.sep_y, c->lvl, c->t);
+}
 
 static inline void rec_ptr(orc_t *o, const rec_t *r, int hc, double **p, int *ld) {
   *p = at(o, r->b, hc, r->lox, r->loy);
@@ -835,6 +851,11 @@ static void fused_dpotrf(ctx_t *c, int hs) {
   for (int64_t i = o->rptr[c->t][b]; i < o->rptr[c->t][b + 1]; i++) {
     const rec_t *a = &o->rec[c->t][i];
     int m = a->hix - a->lox + 1;
+    if (c->log) {
+      fprintf(c->log, "POTRF: {");
+      log_operand(c, "A", "Size", a);
+      log_tail(c, a);
+    }
     if (m == 0) continue;
     c->fl[0] += (double)m * m * m / 3.0 + (double)m * m / 2.0 + (double)m / 6.0;
     c->calls[0]++;
@@ -857,6 +878,12 @@ static void fused_dtrsm(ctx_t *c, int hs, int hp) {
       int m = b->hix - b->lox + 1, n = b->hiy - b->loy + 1;
       c->fl[1] += (double)m * n * n;
       c->calls[1]++;
+      if (c->log) {
+        fprintf(c->log, "TRSM: {");
+        log_operand(c, "A", "Size", a);
+        log_operand(c, "B", "Size", b);
+        log_tail(c, b);
+      }
       if (c->dry) continue;
       double *A, *Bp;
       int lda, ldb;
@@ -895,6 +922,13 @@ static void fused_update(ctx_t *c, int hs, int hp, int hg) {
       const rec_t *cc = find_rec(o, c->t, bC, row * col_cluster_size + col);
       if (!cc) continue;
       int cx = cc->hix - cc->lox + 1;
+      if (c->log && (hg != hp || col <= row)) {
+        fprintf(c->log, "GEMM: {");
+        log_operand(c, "A", "size", a);
+        log_operand(c, "B", "size", b);
+        log_operand(c, "C", "size", cc);
+        log_tail(c, cc);
+      }
       double *A = NULL, *Bp = NULL, *C = NULL;
       int lda = 0, ldb = 0, ldc = 0;
       if (!c->dry) {
@@ -1288,4 +1322,103 @@ int orc_solve(orc_t *o, const double *b, double *x) {
   for (int p = 0; p < o->n; p++) x[o->sepdof[p]] = Bv[p]; /* mmat.rg:1483-1491 */
   free(Bv);
   return 0;
+}
+
+/* ------------------------------------------------------------------ debug trace, the `-d` path
+ * Log grammar: partition_matrix mmat.rg:331,352; partition_separator 396,432; compute_filled_clusters
+ * 1010; fused tasks blas.rg:308,340,405,422,490.  Snapshots: write_blocks (mmat.rg:174-218) after
+ * every fused task of the level loop (mmat.rg:1245-1343), file names from gen_filename (149-172).
+ * verify.debug_factor (verify.py:216-275) replays the log and compares each op's block with its
+ * snapshot.  Serial, program order. */
+static void dbg_clusters(orc_t *o, FILE *log, int hr, int hc, int k, int t) {
+  int rows = has_interval(o, hr, k) ? nc_of(o, hr, k) : -1, cols = has_interval(o, hc, k) ? nc_of(o, hc, k) : -1;
+  fprintf(log, "\t\tPartitioning (%d, %d) Cluster: %d Rows: %d Cols: %d\n", LABEL_OF(o, hr), LABEL_OF(o, hc), k, rows, cols);
+  for (int row = 0; row < rows; row++) {
+    for (int col = 0; col < cols; col++) {
+      rec_t r;
+      cluster_rect(o, hr, hc, k, row * cols + col, &r);
+      long long sx = r.hix - r.lox + 1, sy = r.hiy - r.loy + 1;
+      fprintf(log,
+              "\t\tCluster: {'Block': (%d, %d), 'color': (%d, %d, %d), 'Lo': (%d, %d), 'Hi': (%d, %d), 'size': (%lld, %lld), "
+              "'vol': %lld, 'Interval': %d}\n",
+              LABEL_OF(o, hr), LABEL_OF(o, hc), LABEL_OF(o, hr), LABEL_OF(o, hc), row * cols + col, r.lox, r.loy, r.hix, r.hiy, sx,
+              sy, (sx > 0 && sy > 0) ? sx * sy : 0LL, t);
+    }
+    fprintf(log, "\n");
+  }
+}
+
+static int dbg_snapshot(orc_t *o, const char *dir, const char *name, int full) {
+  char path[2048];
+  snprintf(path, sizeof path, "%s/%s.mtx", dir, name);
+  return orc_write_factor(o, path, full);
+}
+
+int orc_debug_trace(orc_t *o, const char *dir, const char *log_path, int full_precision) {
+  if (!o->analyzed) return fail(o, "analyze first");
+  if (!B.potrf) return fail(o, "no BLAS loaded (orc_set_blas)");
+  FILE *log = fopen(log_path, "w");
+  if (!log) return fail(o, "cannot write %s", log_path);
+  const int L = o->levels;
+  /* partition_matrix, mmat.rg:316-360 */
+  for (int lvl = 0; lvl < L; lvl++)
+    for (int h = 1 << lvl; h < (1 << (lvl + 1)); h++)
+      for (int hr = h; hr >= 1; hr >>= 1)
+        fprintf(log, "Block: {'Block': (%d, %d), 'Lo': (%d, %d), 'Hi': (%d, %d)}\n", LABEL_OF(o, hr), LABEL_OF(o, h), o->start[hr],
+                o->start[h], o->start[hr] + o->sz[hr] - 1, o->start[h] + o->sz[h] - 1);
+  /* compute_filled_clusters, mmat.rg:918-1026: cluster rectangles of every block down to the level
+   * being eliminated, then the filled records of that interval label */
+  for (int t = 0; t < L; t++) {
+    const int lvl = L - 1 - t, k = interval_of_level(o, lvl);
+    for (int l2 = 0; l2 <= lvl; l2++)
+      for (int hr = 1 << l2; hr < (1 << (l2 + 1)); hr++)
+        for (int cl = l2; cl <= lvl; cl++)
+          for (int hc = hr << (cl - l2); hc < ((hr + 1) << (cl - l2)); hc++) dbg_clusters(o, log, hr, hc, k, t);
+    orc_filled_t *f = malloc(sizeof(orc_filled_t) * (size_t)(o->nrec[t] + 1));
+    orc_get_filled(o, t, f);
+    for (int64_t i = 0; i < o->nrec[t]; i++)
+      fprintf(log,
+              "Fill: {'Level': %d, 'Interval': %d, 'Block': (%lld, %lld), 'Cluster': (%lld, %lld, %lld), 'Filled': 0, 'Lo': (%lld, "
+              "%lld), 'Hi': (%lld, %lld), 'Size': (%lld, %lld)}\n",
+              lvl, t, (long long)f[i].sep_x, (long long)f[i].sep_y, (long long)f[i].sep_x, (long long)f[i].sep_y,
+              (long long)f[i].cluster, (long long)f[i].lo_x, (long long)f[i].lo_y, (long long)f[i].hi_x, (long long)f[i].hi_y,
+              (long long)(f[i].hi_x - f[i].lo_x + 1), (long long)(f[i].hi_y - f[i].lo_y + 1));
+    free(f);
+  }
+  if (orc_assemble(o)) {
+    fclose(log);
+    return -1;
+  }
+  if (B.set_threads) B.set_threads(1);
+  char name[256];
+  int rc = 0;
+  for (int lvl = L - 1; lvl >= 0 && !rc; lvl--) {
+    ctx_t c;
+    memset(&c, 0, sizeof c);
+    c.o = o, c.lvl = lvl, c.t = L - 1 - lvl, c.log = log;
+    fprintf(log, "Factoring Level: %d Interval: %d Iteration: %d\n", lvl, interval_of_level(o, lvl), 0);
+    const int first = 1 << lvl, last = (1 << (lvl + 1)) - 1;
+    for (int hs = first; hs <= last && !rc; hs++) {
+      fused_dpotrf(&c, hs);
+      snprintf(name, sizeof name, "potrf_lvl%d_a%d%d", lvl, LABEL_OF(o, hs), LABEL_OF(o, hs));
+      rc = dbg_snapshot(o, dir, name, full_precision);
+    }
+    for (int hs = first; hs <= last && !rc; hs++)
+      for (int hp = hs >> 1; hp >= 1 && !rc; hp >>= 1) {
+        fused_dtrsm(&c, hs, hp);
+        snprintf(name, sizeof name, "trsm_lvl%d_a%d%d_b%d%d", lvl, LABEL_OF(o, hs), LABEL_OF(o, hs), LABEL_OF(o, hp), LABEL_OF(o, hs));
+        rc = dbg_snapshot(o, dir, name, full_precision);
+      }
+    for (int hs = first; hs <= last && !rc; hs++)
+      for (int hp = hs >> 1; hp >= 1 && !rc; hp >>= 1)
+        for (int hg = hp; hg >= 1 && !rc; hg >>= 1) {
+          fused_update(&c, hs, hp, hg);
+          snprintf(name, sizeof name, "gemm_lvl%d_a%d%d_b%d%d_c%d%d", lvl, LABEL_OF(o, hg), LABEL_OF(o, hs), LABEL_OF(o, hp),
+                   LABEL_OF(o, hs), LABEL_OF(o, hg), LABEL_OF(o, hp));
+          rc = dbg_snapshot(o, dir, name, full_precision);
+        }
+  }
+  fprintf(log, "Done factoring Iteration: %d.\n", 0);
+  fclose(log);
+  return rc;
 }

@@ -84,6 +84,11 @@ int orc_solve(orc_t *, const double *b, double *x);
 int orc_read_vector(const char *path, int n, double *out);               /* mnd.c:201-229 */
 int orc_write_solution(const char *path, int n, const double *x);      /* mmat.rg:785-798 */
 
+/* the `-d` debug path: log (mmat.rg:331,352,396,432,1010; blas.rg:308,340,405,422,490) and one
+ * snapshot <dir>/{potrf,trsm,gemm}_lvl*.mtx per fused task (write_blocks, mmat.rg:149-218), in
+ * program order; what verify.debug_factor (verify.py:216-275) replays */
+int orc_debug_trace(orc_t *, const char *dir, const char *log_path, int full_precision);
+
 uint64_t orc_hash_sax(uint64_t key); /* uthash.h:602-610 over the 8 key bytes */
 
 #ifdef __cplusplus

@@ -70,7 +70,7 @@ def lib():
                  "orc_filled_checksum", "orc_factor_nnz_alloc", "orc_flops", "orc_flops_by_level",
                  "orc_call_counts", "orc_assemble", "orc_factor", "orc_factor_levels", "orc_fused_dpotrf",
                  "orc_fused_dtrsm", "orc_fused_update", "orc_factor_nnz", "orc_get_factor_coo",
-                 "orc_get_factor_dense", "orc_write_factor", "orc_solve"):
+                 "orc_get_factor_dense", "orc_write_factor", "orc_solve", "orc_debug_trace"):
         getattr(L, name).argtypes = None  # first arg is the handle; set per call below
     if L.orc_set_blas(find_openblas().encode()) != 0:
         raise RuntimeError("oracle: cannot load host BLAS")
@@ -210,6 +210,13 @@ class Oracle:
 
     def write_factor(self, path, full_precision=False):
         if self.L.orc_write_factor(self.h, path.encode(), C.c_int(1 if full_precision else 0)) != 0:
+            raise RuntimeError(self.err())
+
+    def debug_trace(self, directory, log_path, full_precision=False):
+        """the reference's `-d` run: log + one snapshot per fused task (verify.debug_factor's input)"""
+        os.makedirs(directory, exist_ok=True)
+        if self.L.orc_debug_trace(self.h, directory.encode(), log_path.encode(),
+                                  C.c_int(1 if full_precision else 0)) != 0:
             raise RuntimeError(self.err())
 
     def solve(self, b):
