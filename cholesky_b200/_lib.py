@@ -15,7 +15,7 @@ EXPORTS = [
     "chol_flops", "chol_flops_by_level", "chol_call_counts", "chol_factor_doubles", "chol_assemble", "chol_factor",
     "chol_fused_dpotrf", "chol_fused_dtrsm", "chol_fused_update", "chol_factor_host", "chol_synchronize",
     "chol_kernel_times", "chol_launch_times", "chol_num_launches", "chol_get_launch", "chol_set_partition", "chol_ipc_export",
-    "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor",
+    "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor", "chol_write_factor_binary", "chol_factor_binary_to_mtx",
     "chol_residual", "chol_write_debug_log", "chol_factor_debug", "chol_solve", "chol_matvec", "chol_read_vector", "chol_write_solution",
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size", "mm_typecode_to_str",
     "mnd_read_separators", "mnd_read_clusters", "mnd_read_matrix", "mnd_read_vector", "mnd_hash_sax",

@@ -164,6 +164,10 @@ std::vector<DebugStep> debug_steps(const Problem &P);
 // POTRF / TRSM / GEMM lines of the level loop, in program order (needs Symbolic::records)
 int write_debug_log(const Problem &P, const Symbolic &S, FILE *f, std::string &err);
 
+// binary block dump of the factor (factor_file.cc); the converter back to text is chol_factor_binary_to_mtx
+int write_factor_binary(const Problem &P, const Symbolic &S, const double *fac, int rank, int world, int depth, const char *path,
+                        std::string &err);
+
 uint64_t mix64(uint64_t x);
 uint64_t filled_hash(const FilledRec &r);
 

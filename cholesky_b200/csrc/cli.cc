@@ -1,6 +1,7 @@
 // `cholesky` command line: the reference's flags (mmat.rg:1072-1093) over the C ABI.
 //   -i matrix.mtx -s separators.txt -c clusters.txt [-b rhs.mtx -o solution] [-m factor.mtx]
-//   [-p permuted.mtx] [-d debug_dir] [--iterations N] [--gpu D]
+//   [-p permuted.mtx] [-d debug_dir] [--iterations N] [--gpu D] [--binary-factor factor.bin]
+//   cholesky --convert factor.bin factor.mtx      (binary dump -> the reference's text format, no GPU)
 // Progress lines follow the reference's stdout (mmat.rg:1095-1121, 1228, 1357).
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,12 @@
 int main(int argc, char **argv) {
   const char *mat = "", *sep = "", *clu = "", *bfile = "", *sol = "", *fac = "", *perm = "", *dbg = "";
   int iterations = 1, gpu = 0;
+  const char *binfac = "";
+  if (argc == 4 && !strcmp(argv[1], "--convert")) {
+    int rc = chol_factor_binary_to_mtx(argv[2], argv[3], 0);
+    if (rc) printf("cannot convert %s: error %d\n", argv[2], rc);
+    return rc ? 1 : 0;
+  }
   for (int i = 0; i + 1 < argc; i++) {
     if (!strcmp(argv[i], "-i")) mat = argv[i + 1];
     else if (!strcmp(argv[i], "-s")) sep = argv[i + 1];
@@ -23,6 +30,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "-d")) dbg = argv[i + 1];  // debug_path, debug = true (mmat.rg:1086-1090)
     else if (!strcmp(argv[i], "--iterations")) iterations = atoi(argv[i + 1]);
     else if (!strcmp(argv[i], "--gpu")) gpu = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "--binary-factor")) binfac = argv[i + 1];
   }
   printf("Iterations: %d\n", iterations);
   chol_t *c = nullptr;
@@ -64,6 +72,13 @@ int main(int argc, char **argv) {
   if (*fac) {
     printf("saving matrix to: %s\n\n", fac);
     if (chol_write_factor(c, fac, 0)) {
+      printf("%s\n", chol_last_error(c));
+      return 1;
+    }
+  }
+  if (*binfac) {
+    printf("saving matrix to: %s\n\n", binfac);
+    if (chol_write_factor_binary(c, binfac)) {
       printf("%s\n", chol_last_error(c));
       return 1;
     }

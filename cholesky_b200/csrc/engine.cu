@@ -739,6 +739,11 @@ int chol_write_factor(chol_t *c, const char *path, int full) {
   return write_factor_file(c, path, full);
 }
 
+int chol_write_factor_binary(chol_t *c, const char *path) {
+  if (fetch_factor(c)) return -1;
+  return write_factor_binary(c->P, c->S, c->h_fac.data(), c->rank, c->world, c->D.depth, path, c->err) ? -1 : 0;
+}
+
 // ------------------------------------------------------------------------------ debug trace (`-d`)
 int chol_write_debug_log(chol_t *c, const char *path) {
   if (!c->analyzed) return fail(c, "analyze first");

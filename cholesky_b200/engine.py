@@ -217,6 +217,10 @@ class Cholesky:
     def write_factor(self, path, full_precision=False):
         self._ck(self.L.chol_write_factor(self.h, path.encode(), 1 if full_precision else 0))
 
+    def write_factor_binary(self, path):
+        """binary block dump of the factor (csrc/factor_file.cc); `factor_binary_to_mtx` converts it"""
+        self._ck(self.L.chol_write_factor_binary(self.h, path.encode()))
+
     # ---- debug trace, the `-d` path (mmat.rg:1086-1090; verify.py:216-275 replays it)
     def write_debug_log(self, path=None):
         """the log lines of a debug run (host only; needs analyze(keep_records=True)); None: stdout"""
@@ -256,3 +260,35 @@ def write_solution(path, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     if _lib.load().chol_write_solution(path.encode(), x.size, _p(x)) != 0:
         raise CholeskyError("cannot write " + path)
+
+
+def factor_binary_to_mtx(bin_path, mtx_path, full_precision=False):
+    """streaming conversion of a binary factor dump to the reference's text format (host only)"""
+    rc = _lib.load().chol_factor_binary_to_mtx(bin_path.encode(), mtx_path.encode(), 1 if full_precision else 0)
+    if rc != 0:
+        raise CholeskyError(f"factor_binary_to_mtx({bin_path}): error {rc}")
+
+
+def read_factor_binary(path):
+    """(n, I, J, V) of a binary factor dump: entries != 0, 0-based permuted coordinates"""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:8] != b"CHOLFAC1":
+        raise CholeskyError(path + " is not a factor dump")
+    n, ncols = np.frombuffer(raw, dtype=np.int32, count=2, offset=8)
+    nrec, nnz = np.frombuffer(raw, dtype=np.int64, count=2, offset=24)
+    off = 40
+    I, J, V = [], [], []
+    for _ in range(int(nrec)):
+        r0, c0, nr, nc = np.frombuffer(raw, dtype=np.int32, count=4, offset=off)
+        off += 16
+        v = np.frombuffer(raw, dtype=np.float64, count=int(nr) * int(nc), offset=off).reshape(nc, nr).T
+        off += 8 * int(nr) * int(nc)
+        ii, jj = np.nonzero(v)
+        I.append(ii + r0), J.append(jj + c0), V.append(v[ii, jj])
+    I = np.concatenate(I) if I else np.zeros(0, dtype=np.int64)
+    J = np.concatenate(J) if J else np.zeros(0, dtype=np.int64)
+    V = np.concatenate(V) if V else np.zeros(0)
+    if I.size != nnz:
+        raise CholeskyError(path + ": entry count differs from the header")
+    return int(n), I, J, V

@@ -125,6 +125,12 @@ int64_t chol_factor_nnz(chol_t *);                                           /* 
 int64_t chol_get_factor_coo(chol_t *, int32_t *I, int32_t *J, double *V);   /* 0-based permuted */
 int chol_get_factor_dense(chol_t *, double *out_row_major_nxn);             /* small n only */
 int chol_write_factor(chol_t *, const char *path, int full_precision);     /* "%0.8g" or "%.17g" */
+/* the factor at scale (row f-4): binary block dump (header + one dense record per filled cluster, layout
+ * in csrc/factor_file.cc) and its streaming conversion to write_matrix's text format, host only,
+ * one record in memory at a time.  Converter returns 0, or < 0: -1 cannot read, -2 not a dump,
+ * -3 cannot write, -4 truncated or corrupt, -5 entry count differs from the header. */
+int chol_write_factor_binary(chol_t *, const char *path);
+int chol_factor_binary_to_mtx(const char *bin_path, const char *mtx_path, int full_precision);
 /* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F, W = k Rademacher columns (seeded) */
 int chol_residual(chol_t *, int k, uint64_t seed, double *rel);
 

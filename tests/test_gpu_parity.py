@@ -148,3 +148,24 @@ def test_config3_64cubed_properties():
     st = ch.factor()
     assert st.info == 0
     assert ch.residual(k=2) <= 1e-12
+
+
+@pytest.mark.parametrize("case", ["lapl_400x400", "lapl_3375x3375"])
+def test_binary_factor_dump_round_trip(case, golden, tmp_path):
+    """row f-4: the binary block dump and its streaming converter give the file write_matrix would"""
+    import scipy.io
+    from cholesky_b200 import factor_binary_to_mtx, read_factor_binary
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    ch.factor()
+    b, t, u = str(tmp_path / "f.bin"), str(tmp_path / "f.mtx"), str(tmp_path / "direct.mtx")
+    ch.write_factor_binary(b)
+    n, I, J, V = read_factor_binary(b)
+    Ic, Jc, Vc = ch.factor_coo()
+    assert n == g.n and _coo_dict(I, J, V) == _coo_dict(Ic, Jc, Vc)
+    factor_binary_to_mtx(b, t)
+    ch.write_factor(u)
+    assert sorted(open(t).read().splitlines()[2:]) == sorted(open(u).read().splitlines()[2:])
+    assert open(t).read().splitlines()[:2] == open(u).read().splitlines()[:2]
+    L = np.tril(np.asarray(scipy.io.mmread(t).todense()))
+    assert np.allclose(g.L_dense(), L, rtol=1e-4, atol=1e-4)

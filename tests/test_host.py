@@ -203,3 +203,43 @@ def test_numeric_path_fails_loudly_without_gpu(golden):
     ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
     with pytest.raises(CholeskyError, match="no CUDA device"):
         ch.factor()
+
+
+def test_factor_binary_converter_streams_a_dump_to_the_reference_text_format(tmp_path):
+    """csrc/factor_file.cc: header + dense records -> write_matrix's "%d %d %0.8g" lines (mmat.rg:129-144)"""
+    import struct
+    import scipy.io
+    from cholesky_b200 import CholeskyError, factor_binary_to_mtx, read_factor_binary
+    rng = np.random.default_rng(3)
+    n = 11
+    recs = [(0, 0, 4, 4), (6, 0, 3, 4), (4, 4, 7, 7)]
+    dense = np.zeros((n, n))
+    body = b""
+    for r0, c0, nr, nc in recs:
+        v = rng.standard_normal((nr, nc))
+        if r0 == c0:
+            v = np.tril(v)
+        v[rng.random((nr, nc)) < 0.2] = 0.0
+        dense[r0:r0 + nr, c0:c0 + nc] = v
+        body += struct.pack("<4i", r0, c0, nr, nc) + np.asfortranarray(v).tobytes(order="F")
+    nnz = int(np.count_nonzero(dense))
+    head = b"CHOLFAC1" + struct.pack("<2i", n, n) + b"MCRG" + struct.pack("<i", 0) + struct.pack("<2q", len(recs), nnz)
+    p = tmp_path / "f.bin"
+    p.write_bytes(head + body)
+    factor_binary_to_mtx(str(p), str(tmp_path / "f.mtx"), full_precision=True)
+    got = scipy.io.mmread(str(tmp_path / "f.mtx")).toarray()
+    assert np.array_equal(got, dense)
+    nn, I, J, V = read_factor_binary(str(p))
+    back = np.zeros((n, n))
+    back[I, J] = V
+    assert nn == n and np.array_equal(back, dense)
+    # "%0.8g" by default, as the reference
+    factor_binary_to_mtx(str(p), str(tmp_path / "g.mtx"))
+    assert np.allclose(scipy.io.mmread(str(tmp_path / "g.mtx")).toarray(), dense, rtol=1e-7, atol=0)
+    # truncated and foreign files are refused
+    (tmp_path / "t.bin").write_bytes((head + body)[:-8])
+    with pytest.raises(CholeskyError, match="-4"):
+        factor_binary_to_mtx(str(tmp_path / "t.bin"), str(tmp_path / "t.mtx"))
+    (tmp_path / "x.bin").write_bytes(b"not a dump" * 10)
+    with pytest.raises(CholeskyError, match="-2"):
+        factor_binary_to_mtx(str(tmp_path / "x.bin"), str(tmp_path / "x.mtx"))
