@@ -239,12 +239,28 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
   if (warp == Cfg::kConsumers) {
     // ===== producer warp: lane l < BK copies column l of the A tile, lane BK + l column l of the B tile
     const unsigned a_bytes = (unsigned)(min(BM, (mrem + 1) & ~1) * 8), b_bytes = (unsigned)(min(BN, (nrem + 1) & ~1) * 8);
+    // The epilogue is a read-modify-write of a destination tile that sits in HBM (the trailing matrix is
+    // far larger than L2): the producer pulls the tile's lines into L2 kPrefetchLead stages before the
+    // consumers get there.
+    constexpr int kPrefetchLead = 48;
+    int total = 0;
+    for (int c = 0; c < pr.contrib_count; c++) total += (contribs[pr.contrib_begin + c].K + BK - 1) / BK;
+    const int pf_at = max(0, total - kPrefetchLead);
     int it = 0;
     for (int c = 0; c < pr.contrib_count; c++) {
       const GemmContrib cb = contribs[pr.contrib_begin + c];
       const double *__restrict__ A = fac + cb.a_off + row0;
       const double *__restrict__ Bp = fac + cb.b_off + col0;
       for (int k0 = 0; k0 < cb.K; k0 += BK, it++) {
+        if (it == pf_at) {
+          const int rows = min(BM, mrem);
+          for (int j = lane; j < min(BN, nrem); j += 32) {
+            const char *p0 = reinterpret_cast<const char *>(fac + pr.c_off + row0 + (size_t)(col0 + j) * pr.ldc);
+            const char *p1 = p0 + (size_t)rows * 8;
+            for (const char *q = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127); q < p1; q += 128)
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
+          }
+        }
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
         const int kv = min(BK, cb.K - k0);
@@ -324,19 +340,30 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
   double *__restrict__ C = fac + pr.c_off;
   if (!SHARED) {
     // local destination: read-modify-write straight from the accumulator fragments (measured 2 % faster
-    // on one GPU than staging through shared memory)
+    // on one GPU than staging through shared memory).  All loads of one row block are issued before the
+    // first store: written as `C[..] -= acc` the compiler has to keep every store ahead of the next load
+    // (same array), i.e. 32 dependent round trips to L2/HBM per thread -- ncu's source view had 40 % of
+    // the warp samples of the K = 256 launches on those DADDs, and the DMMA pipe at 82 %.
 #pragma unroll
     for (int i = 0; i < MB; i++) {
       const int r = row0 + wm0 + i * 8 + g;
-      if (r >= pr.M) continue;
+      double cv[NBk][2];
+      bool ok[NBk][2];
 #pragma unroll
-      for (int j = 0; j < NBk; j++) {
+      for (int j = 0; j < NBk; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int cc = col0 + wn0 + j * 8 + 2 * t + e;
-          if (cc < pr.N && (!pr.tri || r >= cc)) C[r + (size_t)cc * pr.ldc] -= acc[i][j][e];
+          ok[j][e] = r < pr.M && cc < pr.N && (!pr.tri || r >= cc);
+          cv[j][e] = ok[j][e] ? C[r + (size_t)cc * pr.ldc] : 0.0;
         }
-      }
+#pragma unroll
+      for (int j = 0; j < NBk; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+          if (ok[j][e]) C[r + (size_t)cc * pr.ldc] = cv[j][e] - acc[i][j][e];
+        }
     }
     return;
   }
