@@ -384,37 +384,66 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
   // 16-byte peer stores when every column of the tile starts on a 16-byte boundary (always true for the
   // in-panel updates; Schur destinations start wherever their cluster starts)
   const bool vec = (((pr.c_off + row0) | pr.ldc) & 1) == 0;
-  for (int j = warp; j < BN; j += Cfg::kConsumers) {
-    const int cc = col0 + j;
-    if (cc >= pr.N) break;
+  // Four columns per step: their loads of C go out together, then the peer stores.  One column at a time,
+  // every load had to wait for the previous column's stores (one of the peers is this rank's own copy).
+  constexpr int kColBatch = 4;
+  for (int jb = warp; jb < BN; jb += Cfg::kConsumers * kColBatch) {
+    if (col0 + jb >= pr.N) break;
     if (vec) {
 #pragma unroll
-      for (int rr = 2 * lane; rr < BM; rr += 64) {
-        const int r = row0 + rr;
-        const bool ok0 = r < pr.M && (!pr.tri || r >= cc), ok1 = r + 1 < pr.M && (!pr.tri || r + 1 >= cc);
-        if (!ok0 && !ok1) continue;
-        const size_t o = r + (size_t)cc * pr.ldc;
-        if (ok0 && ok1) {
-          const double2 cv = *reinterpret_cast<const double2 *>(C + o);
-          const double2 v = make_double2(cv.x - Cs[j * kLdC + rr], cv.y - Cs[j * kLdC + rr + 1]);
+      for (int rr0 = 0; rr0 < BM; rr0 += 64) {
+        const int rr = rr0 + 2 * lane, r = row0 + rr;
+        double2 cv[kColBatch];
+        int okm[kColBatch];  // bit 0: row r is written, bit 1: row r + 1
 #pragma unroll
-          for (int p = 0; p < kMaxPeers; p++)
-            if (p < peers.n) *reinterpret_cast<double2 *>(peers.fac[p] + pr.c_off + o) = v;
-        } else {
-          const int q = ok0 ? 0 : 1;
-          const double v = C[o + q] - Cs[j * kLdC + rr + q];
+        for (int u = 0; u < kColBatch; u++) {
+          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
+          const bool in = j < BN && cc < pr.N;
+          const bool ok0 = in && r < pr.M && (!pr.tri || r >= cc), ok1 = in && r + 1 < pr.M && (!pr.tri || r + 1 >= cc);
+          okm[u] = (ok0 ? 1 : 0) | (ok1 ? 2 : 0);
+          const size_t o = r + (size_t)cc * pr.ldc;
+          cv[u] = make_double2(0.0, 0.0);
+          if (okm[u] == 3) cv[u] = *reinterpret_cast<const double2 *>(C + o);
+          else if (okm[u] == 1) cv[u].x = C[o];
+          else if (okm[u] == 2) cv[u].y = C[o + 1];
+        }
 #pragma unroll
-          for (int p = 0; p < kMaxPeers; p++)
-            if (p < peers.n) peers.fac[p][pr.c_off + o + q] = v;
+        for (int u = 0; u < kColBatch; u++) {
+          if (!okm[u]) continue;
+          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
+          const size_t o = r + (size_t)cc * pr.ldc;
+          const double2 v = make_double2(cv[u].x - Cs[j * kLdC + rr], cv[u].y - Cs[j * kLdC + rr + 1]);
+          if (okm[u] == 3) {
+#pragma unroll
+            for (int p = 0; p < kMaxPeers; p++)
+              if (p < peers.n) *reinterpret_cast<double2 *>(peers.fac[p] + pr.c_off + o) = v;
+          } else {
+            const int q = okm[u] == 1 ? 0 : 1;
+            const double w = q ? v.y : v.x;
+#pragma unroll
+            for (int p = 0; p < kMaxPeers; p++)
+              if (p < peers.n) peers.fac[p][pr.c_off + o + q] = w;
+          }
         }
       }
     } else {
 #pragma unroll
-      for (int rr = lane; rr < BM; rr += 32) {
-        const int r = row0 + rr;
-        if (r < pr.M && (!pr.tri || r >= cc)) {
+      for (int rr0 = 0; rr0 < BM; rr0 += 32) {
+        const int rr = rr0 + lane, r = row0 + rr;
+        double cv[kColBatch];
+        bool ok[kColBatch];
+#pragma unroll
+        for (int u = 0; u < kColBatch; u++) {
+          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
+          ok[u] = j < BN && cc < pr.N && r < pr.M && (!pr.tri || r >= cc);
+          cv[u] = ok[u] ? C[r + (size_t)cc * pr.ldc] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kColBatch; u++) {
+          if (!ok[u]) continue;
+          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
           const size_t o = r + (size_t)cc * pr.ldc;
-          const double v = C[o] - Cs[j * kLdC + rr];
+          const double v = cv[u] - Cs[j * kLdC + rr];
 #pragma unroll
           for (int p = 0; p < kMaxPeers; p++)
             if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
@@ -470,19 +499,29 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmPr
         for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
+  // read-modify-write of the destination: the eight loads of a row block go out together, then the stores
+  // (`C[..] -= acc` would chain 32 load/store round trips, see gemm_grouped_ws)
   double *__restrict__ C = fac + pr.c_off;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int r = row0 + i * 8 + g;
-    if (r >= pr.M) continue;
+    double cv[4][2];
+    bool ok[4][2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int cc = col0 + j * 8 + 2 * t + e;
-        if (cc < pr.N && (!pr.tri || r >= cc)) C[r + (size_t)cc * pr.ldc] -= acc[i][j][e];
+        ok[j][e] = r < pr.M && cc < pr.N && (!pr.tri || r >= cc);
+        cv[j][e] = ok[j][e] ? C[r + (size_t)cc * pr.ldc] : 0.0;
       }
-    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + j * 8 + 2 * t + e;
+        if (ok[j][e]) C[r + (size_t)cc * pr.ldc] = cv[j][e] - acc[i][j][e];
+      }
   }
 }
 
