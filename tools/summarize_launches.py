@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 from bench import WORKLOADS  # noqa: E402
 from cholesky_b200 import Cholesky  # noqa: E402
 
+OURS = ("gemm_grouped", "gemm_small_warp", "potrf_tile", "trsm_tile")  # kernels of the launch table
 PHASE = {1: "fused_dpotrf", 2: "fused_dtrsm", 3: "fused_dpotrf+dtrsm", 4: "fused_dsyrk/dgemm"}
 
 
@@ -24,17 +25,18 @@ def main():
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     scale = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0}
     ours = [(r[ki], float(r[vi].replace(",", "")) * scale[r[ui]]) for r in rows[1:]
-            if any(k in r[ki] for k in ("gemm_grouped", "potrf_tile", "trsm_tile"))]
+            if any(k in r[ki] for k in OURS)]
     other = [(r[ki], float(r[vi].replace(",", "")) * scale[r[ui]]) for r in rows[1:]
-             if not any(k in r[ki] for k in ("gemm_grouped", "potrf_tile", "trsm_tile"))]
+             if not any(k in r[ki] for k in OURS)]
     ch = Cholesky().generate(*WORKLOADS[workload]).analyze()
     ls = [l for l in ch.launches() if l["kind"] in ("gemm_grouped", "potrf_tile", "trsm_tile")]
     n = min(len(ls), len(ours))
     agg = collections.OrderedDict()
     tot = 0.0
     for l, (name, ms) in zip(ls[:n], ours[:n]):
-        assert l["kind"] in name, (l, name)
-        key = (l["kind"] + ("/128" if l["cfg"] == 1 else ""), l["level"], PHASE[l["phase"]])
+        want = "gemm_small_warp" if (l["kind"] == "gemm_grouped" and l["cfg"] == 3) else l["kind"]
+        assert want in name, (l, name)
+        key = (want + ("/128" if l["cfg"] == 1 else ""), l["level"], PHASE[l["phase"]])
         a = agg.setdefault(key, [0, 0.0, 0.0, 0])
         a[0] += 1
         a[1] += ms
