@@ -16,7 +16,7 @@ EXPORTS = [
     "chol_fused_dpotrf", "chol_fused_dtrsm", "chol_fused_update", "chol_factor_host", "chol_synchronize",
     "chol_kernel_times", "chol_launch_times", "chol_num_launches", "chol_get_launch", "chol_set_partition", "chol_ipc_export",
     "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor", "chol_write_factor_binary", "chol_factor_binary_to_mtx",
-    "chol_residual", "chol_write_debug_log", "chol_factor_debug", "chol_solve", "chol_matvec", "chol_read_vector", "chol_write_solution",
+    "chol_residual", "chol_write_debug_log", "chol_factor_debug", "chol_solve", "chol_solve_top_size", "chol_solve_forward", "chol_solve_backward", "chol_solve_stats", "chol_matvec", "chol_read_vector", "chol_write_solution",
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size", "mm_typecode_to_str",
     "mnd_read_separators", "mnd_read_clusters", "mnd_read_matrix", "mnd_read_vector", "mnd_hash_sax",
 ]
@@ -46,7 +46,7 @@ def load():
     L.mnd_hash_sax.restype = C.c_uint64
     L.mnd_hash_sax.argtypes = [C.c_uint64]
     for name in ("chol_nz", "chol_num_blocks", "chol_num_clusters0", "chol_get_block_bounds", "chol_num_filled",
-                 "chol_get_filled", "chol_factor_doubles", "chol_num_launches", "chol_launch_times", "chol_factor_nnz", "chol_get_factor_coo",
+                 "chol_get_filled", "chol_factor_doubles", "chol_solve_top_size", "chol_num_launches", "chol_launch_times", "chol_factor_nnz", "chol_get_factor_coo",
                  "mnd_read_clusters"):
         getattr(L, name).restype = C.c_int64
     _lib = L

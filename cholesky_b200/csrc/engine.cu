@@ -914,7 +914,7 @@ static int ensure_solve(chol_t *c) {
   if (c->solve && c->solve->ready) return 0;
   free_solve(c);
   SolveDev *v = c->solve = new SolveDev();
-  if (build_solve(c->P, c->S, v->V, c->err)) return -1;
+  if (build_solve(c->P, c->S, v->V, c->rank, c->world, c->err)) return -1;
   if (upload(c, &v->tiles, v->V.tiles) || upload(c, &v->gemv, v->V.gemv) || upload(c, &v->gemv_tiles, v->V.gemv_tiles) ||
       upload(c, &v->pull, v->V.pull) || upload(c, &v->pull_contrib, v->V.pull_contrib) || upload(c, &v->pull_tiles, v->V.pull_tiles) ||
       upload(c, &v->gather, v->V.gather) || upload(c, &v->gather_tiles, v->V.gather_tiles) || upload(c, &v->rowmap, v->V.rowmap) ||
@@ -927,18 +927,13 @@ static int ensure_solve(chol_t *c) {
 }
 extern "C" {
 
-/* mmat.rg:1364-1495: permute b, forward substitution leaves -> root, backward root -> leaves, un-permute.
- * Every step is a CUDA kernel on the factor as it sits in HBM (csrc/solve_kernels.cuh). */
-int chol_solve(chol_t *c, const double *b, double *x) {
-  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
-  if (c->world > 1) return fail(c, "chol_solve runs on a single-GPU handle (the factor of a partitioned run is distributed)");
-  if (ensure_solve(c)) return -1;
+// launches [from, to) of the solve schedule on the handle's stream (every step is a CUDA kernel on the
+// factor as it sits in HBM, csrc/solve_kernels.cuh)
+static void run_solve_launches(chol_t *c, size_t from, size_t to) {
   SolveDev *v = c->solve;
-  const int n = c->P.n;
   cudaStream_t st = c->stream;
-  CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-  permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
-  for (const SolveLaunch &l : v->V.launches) {
+  for (size_t i = from; i < to; i++) {
+    const SolveLaunch &l = v->V.launches[i];
     const unsigned g = (unsigned)l.count;
     switch (l.kind) {
       case SK_TILE_F:
@@ -959,12 +954,96 @@ int chol_solve(chol_t *c, const double *b, double *x) {
       case SK_GATHER:
         solve_gather<<<g, kSolveColG * 32, 0, st>>>(v->gather, v->gather_tiles + l.begin, v->rowmap, c->d_fac, v->x);
         break;
+      case SK_EXCHANGE:
+        break;
     }
   }
+}
+static size_t solve_exchange_index(const SolveSchedule &V) {
+  for (size_t i = 0; i < V.launches.size(); i++)
+    if (V.launches[i].kind == SK_EXCHANGE) return i;
+  return V.launches.size();
+}
+
+/* mmat.rg:1364-1495: permute b, forward substitution leaves -> root, backward root -> leaves, un-permute. */
+int chol_solve(chol_t *c, const double *b, double *x) {
+  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+  if (c->world > 1)
+    return fail(c, "chol_solve runs on a single-GPU handle; on a partitioned handle use chol_solve_forward / chol_solve_backward "
+                   "with a sum of the top part over the ranks in between");
+  if (ensure_solve(c)) return -1;
+  SolveDev *v = c->solve;
+  const int n = c->P.n;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
+  run_solve_launches(c, 0, v->V.launches.size());
   permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->x, v->perm, n, v->io);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(x, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* The same sweeps on a partitioned handle (one process per GPU, section 6 of DESIGN.md).  Forward: the rank's
+ * subtree; its pulls leave in the top rows only this rank's contributions (rank 0 starts them from b, the
+ * others from zero), so the SUM of top_partial over the ranks is the right-hand side the top levels see. */
+int64_t chol_solve_top_size(chol_t *c) {
+  if (!c->analyzed) return -1;
+  if (c->world == 1) return 0;
+  return (int64_t)c->P.n - c->P.start[(1 << c->D.depth) - 1];
+}
+int chol_solve_forward(chol_t *c, const double *b, double *top_partial) {
+  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+  if (ensure_solve(c)) return -1;
+  SolveDev *v = c->solve;
+  const int n = c->P.n, t0 = v->V.top_row0;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
+  if (c->rank != 0 && t0 < n) CK(cudaMemsetAsync(v->x + t0, 0, (size_t)(n - t0) * sizeof(double), st));
+  run_solve_launches(c, 0, solve_exchange_index(v->V));
+  CK(cudaGetLastError());
+  if (t0 < n) CK(cudaMemcpyAsync(top_partial, v->x + t0, (size_t)(n - t0) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+/* top_sum: the sum of every rank's top_partial.  x_owned (original dof order): the entries of the rank's own
+ * separators (rank 0: also of the shared top), zeros elsewhere, so that the sum over the ranks is the solution. */
+int chol_solve_backward(chol_t *c, const double *top_sum, double *x_owned) {
+  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+  if (!c->solve || !c->solve->ready) return fail(c, "chol_solve_forward first");
+  SolveDev *v = c->solve;
+  const Problem &P = c->P;
+  const int n = P.n, t0 = v->V.top_row0;
+  cudaStream_t st = c->stream;
+  if (t0 < n) CK(cudaMemcpyAsync(v->x + t0, top_sum, (size_t)(n - t0) * sizeof(double), cudaMemcpyHostToDevice, st));
+  run_solve_launches(c, solve_exchange_index(v->V), v->V.launches.size());
+  permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->x, v->perm, n, v->io);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(x_owned, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (c->world > 1)
+    for (int h = 1; h <= P.N; h++) {
+      const int lv = P.level_of(h), own = lv < c->D.depth ? -1 : (h >> (lv - c->D.depth)) - (1 << c->D.depth);
+      if (own == c->rank || (own < 0 && c->rank == 0)) continue;
+      for (int i = 0; i < P.sz[h]; i++) x_owned[P.perm[P.start[h] + i]] = 0.0;
+    }
+  return 0;
+}
+/* what the rank's solve schedule covers, [0..5] on its subtree levels and [6..11] on the shared top levels:
+ * forward tiles, forward gemv slabs, pull slabs, gather column groups, backward tiles, backward gemv groups */
+int chol_solve_stats(chol_t *c, double *out12) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  SolveSchedule V;
+  if (build_solve(c->P, c->S, V, c->rank, c->world, c->err)) return -1;
+  for (int i = 0; i < 12; i++) out12[i] = 0;
+  for (const SolveLaunch &l : V.launches) {
+    if (l.kind == SK_EXCHANGE) continue;
+    const int slot = l.kind == SK_TILE_F ? 0 : l.kind == SK_GEMV_F ? 1 : l.kind == SK_PULL ? 2 : l.kind == SK_GATHER ? 3 : l.kind == SK_TILE_B ? 4 : 5;
+    const bool top = c->world > 1 && l.level < V.depth;
+    out12[slot + (top ? 6 : 0)] += (double)l.count;
+  }
   return 0;
 }
 

@@ -18,9 +18,26 @@ struct SegRef {
 };
 }  // namespace
 
-int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::string &err) {
+int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, int rank, int world, std::string &err) {
   V = SolveSchedule();
   const int L = P.levels;
+  // Partitioned handle (world = 2^depth ranks, schedule.cc): a rank sweeps the separators of its own
+  // subtree on tree levels >= depth and every separator of the shared top levels (all ranks hold
+  // identical top panels after the factorization).  Between the two parts of the forward sweep the top
+  // rows of the right-hand side are summed over the ranks (SK_EXCHANGE): the pulls of a subtree only
+  // carry that subtree's contributions to them.
+  int depth = 0;
+  while ((1 << depth) < world) depth++;
+  if ((1 << depth) != world || rank < 0 || rank >= world || depth >= L) return err = "bad partition for the solve schedule", -1;
+  V.rank = rank, V.world = world, V.depth = depth;
+  V.top_row0 = world > 1 ? P.start[(1 << depth) - 1] : P.n;  // top separators carry the highest labels: the last rows
+  auto level_range = [&](int lvl, int &h0, int &h1) {
+    h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    if (world > 1 && lvl >= depth) {
+      h0 = ((1 << depth) + rank) << (lvl - depth);
+      h1 = h0 + (1 << (lvl - depth));
+    }
+  };
   // row map of the off-diagonal part of every panel
   std::vector<int64_t> map_off(P.N + 2, 0);
   for (int h = 1; h <= P.N; h++) {
@@ -40,7 +57,9 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
   // ---- forward: leaves to root
   std::vector<SegRef> refs;
   for (int lvl = L - 1; lvl >= 0; lvl--) {
-    const int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    int h0, h1;
+    level_range(lvl, h0, h1);
+    if (world > 1 && lvl == depth - 1) V.launches.push_back(SolveLaunch{SK_EXCHANGE, 0, 0, lvl});
     int maxn = 0;
     for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
     for (int d0 = 0; d0 < maxn; d0 += NB) {
@@ -50,7 +69,7 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
         if (n <= d0) continue;
         V.tiles.push_back(SolveTile{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
       }
-      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_F, b, (int64_t)V.tiles.size() - b});
+      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_F, b, (int64_t)V.tiles.size() - b, lvl});
       int64_t gb = (int64_t)V.gemv_tiles.size();
       for (int h = h0; h < h1; h++) {
         int n = P.sz[h], ld = S.ld[h];
@@ -60,7 +79,7 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
         int g = add_gemv(SolveGemv{S.poff[h] + (d0 + dw) + (int64_t)d0 * ld, ld, rows, dw, P.start[h] + d0, P.start[h] + d0 + dw, 0});
         for (int s = 0; s < (rows + SLAB - 1) / SLAB; s++) V.gemv_tiles.push_back(TileRef{g, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
       }
-      if ((int64_t)V.gemv_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GEMV_F, gb, (int64_t)V.gemv_tiles.size() - gb});
+      if ((int64_t)V.gemv_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GEMV_F, gb, (int64_t)V.gemv_tiles.size() - gb, lvl});
     }
     // ancestors pull the level's contributions: all segments that hit one ancestor row cluster
     refs.clear();
@@ -83,12 +102,13 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
       for (int s = 0; s < (d.rows + SLAB - 1) / SLAB; s++) V.pull_tiles.push_back(TileRef{(int)V.pull.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
       i = j;
     }
-    if ((int64_t)V.pull_tiles.size() > pb) V.launches.push_back(SolveLaunch{SK_PULL, pb, (int64_t)V.pull_tiles.size() - pb});
+    if ((int64_t)V.pull_tiles.size() > pb) V.launches.push_back(SolveLaunch{SK_PULL, pb, (int64_t)V.pull_tiles.size() - pb, lvl});
   }
 
   // ---- backward: root to leaves
   for (int lvl = 0; lvl < L; lvl++) {
-    const int h0 = 1 << lvl, h1 = 1 << (lvl + 1);
+    int h0, h1;
+    level_range(lvl, h0, h1);
     int maxn = 0;
     for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
     int64_t gb = (int64_t)V.gather_tiles.size();
@@ -98,7 +118,7 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
       V.gather.push_back(GatherDesc{S.poff[h] + r0, map_off[h], S.ld[h], nrows, n, P.start[h]});
       for (int g = 0; g < (n + COLG - 1) / COLG; g++) V.gather_tiles.push_back(TileRef{(int)V.gather.size() - 1, (uint16_t)(g & 0xffff), (uint16_t)(g >> 16)});
     }
-    if ((int64_t)V.gather_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GATHER, gb, (int64_t)V.gather_tiles.size() - gb});
+    if ((int64_t)V.gather_tiles.size() > gb) V.launches.push_back(SolveLaunch{SK_GATHER, gb, (int64_t)V.gather_tiles.size() - gb, lvl});
     const int nblk = (maxn + NB - 1) / NB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
       const int d0 = blk * NB;
@@ -108,7 +128,7 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
         if (n <= d0) continue;
         V.tiles.push_back(SolveTile{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
       }
-      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_B, b, (int64_t)V.tiles.size() - b});
+      if ((int64_t)V.tiles.size() > b) V.launches.push_back(SolveLaunch{SK_TILE_B, b, (int64_t)V.tiles.size() - b, lvl});
       if (d0 == 0) continue;
       int64_t tb = (int64_t)V.gemv_tiles.size();
       for (int h = h0; h < h1; h++) {
@@ -118,7 +138,7 @@ int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::stri
         int g = add_gemv(SolveGemv{S.poff[h] + d0, ld, d0, dw, P.start[h] + d0, P.start[h], 0});
         for (int s = 0; s < (d0 + COLG - 1) / COLG; s++) V.gemv_tiles.push_back(TileRef{g, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
       }
-      if ((int64_t)V.gemv_tiles.size() > tb) V.launches.push_back(SolveLaunch{SK_GEMV_B, tb, (int64_t)V.gemv_tiles.size() - tb});
+      if ((int64_t)V.gemv_tiles.size() > tb) V.launches.push_back(SolveLaunch{SK_GEMV_B, tb, (int64_t)V.gemv_tiles.size() - tb, lvl});
     }
   }
   return 0;

@@ -32,10 +32,11 @@ struct GatherDesc {  // x[x0 + c] -= sum_{r < nrows} P[r, c] x[rowmap[map_off + 
   int64_t p_off, map_off;
   int ld, nrows, n, x0;
 };
-enum SolveKind { SK_TILE_F = 0, SK_GEMV_F = 1, SK_PULL = 2, SK_GATHER = 3, SK_TILE_B = 4, SK_GEMV_B = 5 };
+enum SolveKind { SK_TILE_F = 0, SK_GEMV_F = 1, SK_PULL = 2, SK_GATHER = 3, SK_TILE_B = 4, SK_GEMV_B = 5, SK_EXCHANGE = 6 };
 struct SolveLaunch {
   int kind;
   int64_t begin, count;  // range in tiles_f / gemv_tiles / pull_tiles / gather_tiles / tiles_b
+  int level;             // tree level the launch works on
 };
 struct SolveSchedule {
   std::vector<SolveTile> tiles;       // indexed directly by SK_TILE_* launches
@@ -47,9 +48,11 @@ struct SolveSchedule {
   std::vector<GatherDesc> gather;
   std::vector<TileRef> gather_tiles;  // (gather desc, column group)
   std::vector<int> rowmap;            // global permuted row of every stored off-diagonal panel row (-1: padding)
-  std::vector<SolveLaunch> launches;
+  std::vector<SolveLaunch> launches;  // partitioned handles: one SK_EXCHANGE splits the forward sweep (solve.cc)
+  int rank = 0, world = 1, depth = 0;
+  int top_row0 = 0;  // first permuted row of the shared top separators (== n on a single-GPU handle)
 };
 
-int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, std::string &err);
+int build_solve(const Problem &P, const Symbolic &S, SolveSchedule &V, int rank, int world, std::string &err);
 
 }  // namespace chb

@@ -48,3 +48,23 @@ def max_over_ranks(x):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     return x
+
+
+def _sum_over_ranks(a):
+    """element-wise sum of a float64 numpy array over the ranks (bootstrap-grade: staged through torch)"""
+    import numpy as np
+    if not dist.is_initialized() or dist.get_world_size() == 1 or a.size == 0:
+        return a
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def solve(ch, b):
+    """A x = b on a partitioned factor (mmat.rg:1364-1495 over the ranks' subtrees): every rank passes the
+    same b and gets the whole x.  The sweeps run on each rank's GPU; two small host-staged sums cross the
+    ranks -- the top part of the right-hand side after the subtree forward sweeps (chol_solve_top_size
+    doubles) and the assembly of the owned pieces of x at the end."""
+    top = _sum_over_ranks(ch.solve_forward(b))
+    return _sum_over_ranks(ch.solve_backward(top))

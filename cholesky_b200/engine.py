@@ -248,6 +248,32 @@ class Cholesky:
         self._ck(self.L.chol_solve(self.h, _p(b), _p(x)))
         return x
 
+    # ---- solve on a partitioned handle (see cholesky_b200/distributed.py: solve)
+    def solve_top_size(self):
+        return int(self.L.chol_solve_top_size(self.h))
+
+    def solve_forward(self, b):
+        """forward sweep of this rank's subtree; returns its contribution to the shared top rows"""
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+        top = np.zeros(max(self.solve_top_size(), 1), dtype=np.float64)
+        self._ck(self.L.chol_solve_forward(self.h, _p(b), _p(top)))
+        return top[:self.solve_top_size()]
+
+    def solve_backward(self, top_sum):
+        """top levels + backward sweep of the subtree; returns the entries of x this rank owns (zeros elsewhere)"""
+        t = np.ascontiguousarray(top_sum, dtype=np.float64).reshape(-1)
+        if t.size == 0:
+            t = np.zeros(1)
+        x = np.zeros(self.n, dtype=np.float64)
+        self._ck(self.L.chol_solve_backward(self.h, _p(t), _p(x)))
+        return x
+
+    def solve_stats(self):
+        out = np.zeros(12, dtype=np.float64)
+        self._ck(self.L.chol_solve_stats(self.h, _p(out)))
+        keys = ("tiles_fwd", "gemv_fwd", "pull", "gather", "tiles_bwd", "gemv_bwd")
+        return dict(subtree={k: int(v) for k, v in zip(keys, out[:6])}, top={k: int(v) for k, v in zip(keys, out[6:])})
+
 
 def read_vector(path, n):
     out = np.zeros(n, dtype=np.float64)

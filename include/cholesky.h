@@ -145,7 +145,16 @@ int chol_write_debug_log(chol_t *, const char *log_path);
 int chol_factor_debug(chol_t *, const char *dir, int full_precision, int with_txt);
 
 /* ---- solve (next row f-1).  replaces: mmat.rg:1364-1495, blas.rg:217-290, mnd.c:201-229 */
-int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out */
+int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out; single-GPU handle */
+/* the same sweeps on a partitioned handle (after chol_set_partition / chol_ipc_import / chol_factor): every
+ * rank calls chol_solve_forward with the whole b and gets its contribution to the shared top rows
+ * (chol_solve_top_size doubles); the caller sums those over the ranks (any host-side all-reduce) and hands
+ * the sum to chol_solve_backward, which returns the entries of x the rank owns (original dof order, zeros
+ * elsewhere: the sum over the ranks is x).  On a single-GPU handle the pair equals chol_solve. */
+int64_t chol_solve_top_size(chol_t *);
+int chol_solve_forward(chol_t *, const double *b, double *top_partial);
+int chol_solve_backward(chol_t *, const double *top_sum, double *x_owned);
+int chol_solve_stats(chol_t *, double *out12); /* tiles of the rank's solve schedule: [0..5] subtree, [6..11] shared top */
 int chol_matvec(chol_t *, const double *x, double *y); /* host check helper: y = A x, original dof order */
 int chol_read_vector(const char *path, int n, double *out);
 int chol_write_solution(const char *path, int n, const double *x);

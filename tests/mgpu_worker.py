@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cholesky_b200 import Cholesky  # noqa: E402
-from cholesky_b200.distributed import exchange_peers, make_partitioned, max_over_ranks  # noqa: E402
+from cholesky_b200.distributed import exchange_peers, make_partitioned, max_over_ranks, solve  # noqa: E402
 
 
 def main():
@@ -25,6 +25,9 @@ def main():
     exchange_peers(ch)
     st = ch.factor(iterations=2, warmup=1)
     secs = max_over_ranks(st.seconds_best)
+    # triangular solve on the partitioned factor (every rank gets the whole x)
+    rhs = np.random.default_rng(0).integers(1, 11, size=ch.n).astype(np.float64)
+    x = solve(ch, rhs)
     I, J, V = ch.factor_coo()
     parts = [None] * world
     dist.all_gather_object(parts, (I, J, V, ch.partition_stats()))
@@ -51,6 +54,12 @@ def main():
             worst = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.abs(b).max())))
             ok = worst <= 1e-10
             msg = f"worst entry error {worst:.3e}"
+        if ok:
+            xo = ref.solve(rhs)
+            sworst = float(np.max(np.abs(x - xo)) / np.max(np.abs(xo)))
+            res = float(np.linalg.norm(rhs - ch.matvec(x)) / np.linalg.norm(rhs))
+            ok = sworst <= 1e-10 and res <= 1e-12
+            msg += f"; solve vs oracle {sworst:.3e}, residual {res:.3e}"
         print(json.dumps({"ok": bool(ok), "msg": msg, "world": world, "grid": grid, "seconds": secs,
                           "gflops": ch.flops() / secs * 1e-9, "shared_launches": [p[3]["shared_launches"] for p in parts]}))
     flag = torch.tensor([1 if ok else 0], device="cuda")

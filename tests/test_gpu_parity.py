@@ -169,3 +169,21 @@ def test_binary_factor_dump_round_trip(case, golden, tmp_path):
     assert open(t).read().splitlines()[:2] == open(u).read().splitlines()[:2]
     L = np.tril(np.asarray(scipy.io.mmread(t).todense()))
     assert np.allclose(g.L_dense(), L, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["lapl_25x25", "lapl_3375x3375"])
+def test_solve_pair_equals_solve_on_a_single_gpu_handle(case, golden):
+    """chol_solve_forward / chol_solve_backward (the partitioned-handle entry points): with one rank there
+    is no shared top, the pair is chol_solve bit for bit and agrees with the oracle's dtrsv/dgemv sweep"""
+    g = golden[case]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    ch.factor()
+    b = read_vector(g.b, g.n)
+    assert ch.solve_top_size() == 0
+    top = ch.solve_forward(b)
+    assert top.size == 0
+    x2 = ch.solve_backward(top)
+    assert np.array_equal(x2, ch.solve(b))
+    o = orc.Oracle(g.mtx, g.ord, g.clust)
+    o.factor(threads=1)
+    assert np.max(np.abs(x2 - o.solve(b))) <= 1e-10 * np.max(np.abs(x2))

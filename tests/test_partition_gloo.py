@@ -29,14 +29,16 @@ def _worker(rank, world, port, q):
         from cholesky_b200 import Cholesky
         from cholesky_b200.distributed import make_partitioned, max_over_ranks
         ch = make_partitioned(grid=GRID)
-        mine = dict(rank=rank, stats=ch.partition_stats(), launches=ch.launches(), flops=ch.flops(),
+        mine = dict(rank=rank, stats=ch.partition_stats(), launches=ch.launches(), flops=ch.flops(), solve=ch.solve_stats(),
+                    top_size=ch.solve_top_size(),
                     checksums=[ch.filled_checksum(t) for t in range(ch.levels)], nz=ch.nz, levels=ch.levels)
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         assert max_over_ranks(float(rank)) == world - 1
         if rank == 0:
             single = Cholesky().generate(*GRID).analyze()
-            q.put(dict(ranks=gathered, single=dict(launches=single.launches(), stats=single.partition_stats())))
+            q.put(dict(ranks=gathered, single=dict(launches=single.launches(), stats=single.partition_stats(),
+                                                   solve=single.solve_stats(), sizes=single.sep_sizes().tolist())))
     finally:
         dist.destroy_process_group()
 
@@ -86,6 +88,25 @@ def test_partition_covers_single_rank_schedule(world):
         assert sum(l["kind"] == "allreduce_top" for l in r["launches"]) == world - 1
         assert sum(l["kind"] == "peer_barrier" for l in r["launches"]) == r["stats"]["shared_launches"] + 2
         assert r["stats"]["top_doubles"] == ranks[0]["stats"]["top_doubles"] > 0
+
+
+    # the solve schedule (solve.cc): subtree levels split with no overlap, top levels replicated, and the top
+    # part of the right-hand side that crosses the ranks is exactly the rows of the shared separators
+    one = single["solve"]
+    assert one["top"] == {k: 0 for k in one["top"]}
+    split = {k: sum(r["solve"]["subtree"][k] for r in ranks) for k in one["subtree"]}
+    tops = [r["solve"]["top"] for r in ranks]
+    assert all(t == tops[0] for t in tops)
+    # pulls of the level just below the top hit the same destination cluster from several subtrees, so the
+    # split schedules may hold more pull slabs than the single one; everything else adds up exactly
+    for k in one["subtree"]:
+        if k == "pull":
+            assert split[k] + tops[0][k] >= one["subtree"][k]
+        else:
+            assert split[k] + tops[0][k] == one["subtree"][k], k
+    nsep = len(single["sizes"])
+    top_rows = sum(single["sizes"][nsep - (world - 1):])   # the world - 1 highest labels are the shared separators
+    assert all(r["top_size"] == top_rows for r in ranks) and top_rows > 0
 
 
 def test_partition_rejects_bad_world():
