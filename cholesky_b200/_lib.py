@@ -12,7 +12,7 @@ EXPORTS = [
     "chol_generate", "chol_write_inputs", "chol_analyze", "chol_n", "chol_nz", "chol_levels",
     "chol_num_separators", "chol_max_int_size", "chol_num_blocks", "chol_num_clusters0", "chol_get_perm",
     "chol_get_sep_sizes", "chol_get_block_bounds", "chol_num_filled", "chol_get_filled", "chol_filled_checksum",
-    "chol_flops", "chol_flops_by_level", "chol_call_counts", "chol_factor_doubles", "chol_assemble", "chol_factor",
+    "chol_flops", "chol_flops_by_level", "chol_call_counts", "chol_factor_doubles", "chol_level_bytes", "chol_assemble", "chol_factor",
     "chol_fused_dpotrf", "chol_fused_dtrsm", "chol_fused_update", "chol_factor_host", "chol_synchronize",
     "chol_kernel_times", "chol_launch_times", "chol_num_launches", "chol_get_launch", "chol_set_partition", "chol_ipc_export",
     "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor", "chol_write_factor_binary", "chol_factor_binary_to_mtx",

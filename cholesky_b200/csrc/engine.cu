@@ -619,6 +619,38 @@ int chol_partition_stats(chol_t *c, double *out6) {
   out6[0] = a, out6[1] = f, out6[2] = sh, out6[3] = (double)c->D.top_doubles, out6[4] = pt, out6[5] = ts;
   return 0;
 }
+/* Algorithmic HBM bytes of one tree level (8 B x distinct clusters read + written, read-modify-
+ * written clusters counted twice): [0] panels of the level's separators, factored in place (pivot block
+ * lower triangle + filled off-diagonal rows, 16 B per entry); [1] operands of the level's Schur updates
+ * (every filled off-diagonal row cluster once, 8 B per entry); [2] their destination clusters (16 B per
+ * entry, lower triangle only on diagonal clusters).  Single-GPU handles. */
+int chol_level_bytes(chol_t *c, int lvl, double *out3) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
+  const Problem &P = c->P;
+  const Symbolic &S = c->S;
+  double panel = 0, oper = 0, dest = 0;
+  for (int h = 1 << lvl; h < (1 << (lvl + 1)); h++) {
+    const double n = P.sz[h];
+    double off = 0;
+    for (int64_t s = S.seg_ptr[h] + 1; s < S.seg_ptr[h + 1]; s++) off += S.segs[s].hi - S.segs[s].lo;
+    panel += 16.0 * (n * (n + 1) / 2 + off * n);
+    oper += 8.0 * off * n;
+  }
+  for (const Launch &l : c->D.launches) {
+    if (l.level != lvl || l.kind != K_GEMM || l.phase != PH_UPDATE) continue;
+    int last = -1;
+    for (int64_t t = l.begin; t < l.begin + l.count; t++) {
+      const int p = c->D.tiles[t].prob;
+      if (p == last) continue;  // the tiles of one problem are consecutive
+      last = p;
+      const GemmProblem &g = c->D.probs[p];
+      dest += 16.0 * ((double)g.M * g.N - (g.tri ? 0.5 * g.N * (g.N - 1.0) : 0.0));
+    }
+  }
+  out3[0] = panel, out3[1] = oper, out3[2] = dest;
+  return 0;
+}
 int chol_rank(chol_t *c) { return c->rank; }
 int chol_world(chol_t *c) { return c->world; }
 

@@ -115,6 +115,12 @@ class Cholesky:
         self.L.chol_call_counts(self.h, _p(c))
         return dict(potrf=int(c[0]), trsm=int(c[1]), syrk=int(c[2]), gemm=int(c[3]))
 
+    def level_bytes(self, lvl):
+        """algorithmic HBM bytes of a tree level: panels (in-place factorization), Schur operands, destinations"""
+        out = np.zeros(3, dtype=np.float64)
+        self._ck(self.L.chol_level_bytes(self.h, lvl, _p(out)))
+        return dict(panel=float(out[0]), operands=float(out[1]), destinations=float(out[2]))
+
     def factor_doubles(self):
         return int(self.L.chol_factor_doubles(self.h))
 

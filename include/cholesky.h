@@ -82,6 +82,9 @@ double chol_flops(chol_t *);
 int chol_flops_by_level(chol_t *, double *potrf, double *trsm, double *syrk, double *gemm);
 int chol_call_counts(chol_t *, int64_t *c4);                /* reference BLAS calls: potrf, trsm, syrk, gemm */
 int64_t chol_factor_doubles(chol_t *);                      /* device doubles of factor storage */
+/* algorithmic HBM bytes of one tree level: [0] its panels (factored in place), [1] distinct operands of its
+ * Schur updates, [2] their destination clusters (read-modify-written) -- the numerators of the HBM roofline */
+int chol_level_bytes(chol_t *, int lvl, double *out3);
 
 /* ---- numeric factorization on the GPU.  replaces: the level loop mmat.rg:1211-1358 and the
  * fused leaf tasks blas.rg:292-504.  chol_factor = `iterations` x (assemble; level loop), timing

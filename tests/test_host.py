@@ -243,3 +243,21 @@ def test_factor_binary_converter_streams_a_dump_to_the_reference_text_format(tmp
     (tmp_path / "x.bin").write_bytes(b"not a dump" * 10)
     with pytest.raises(CholeskyError, match="-2"):
         factor_binary_to_mtx(str(tmp_path / "x.bin"), str(tmp_path / "x.mtx"))
+
+
+def test_level_bytes_add_up_to_the_factor_storage(golden):
+    """chol_level_bytes: the panel term counts every stored entry of the level's separators once (x 16 B)"""
+    fx = golden["lapl_3375x3375"]
+    ch = Cholesky().load(fx.mtx, fx.ord, fx.clust).analyze()
+    tot = sum(ch.level_bytes(l)["panel"] for l in range(ch.levels))
+    sizes = ch.sep_sizes()
+    # stored entries = nnz(L) pattern of the filled clusters: lower triangles of the pivot blocks + off-diagonal rows
+    assert tot / 16 >= fx.struct["nnzL"]
+    assert tot / 16 <= ch.factor_doubles()
+    root = ch.level_bytes(0)
+    n0 = int(sizes[-1])
+    assert root["panel"] == 16.0 * n0 * (n0 + 1) / 2 and root["operands"] == 0 and root["destinations"] == 0
+    leaves = ch.level_bytes(ch.levels - 1)
+    assert leaves["operands"] > 0 and leaves["destinations"] > 0
+    with pytest.raises(RuntimeError):
+        ch.level_bytes(ch.levels)
