@@ -102,3 +102,23 @@ def test_unmodified_verify_debug_factor_accepts_the_oracle_trace(case, golden, t
     assert raised and seen == files[:len(seen)] and len(seen) == len(files) - 1
     N = fx.struct["nsep"]
     assert seen[-1].endswith(f"_c{N}{N}.mtx") and "lvl1" in seen[-1]
+
+
+@pytest.mark.parametrize("grid", [(3, 3, 1, 5, 3), (5, 4, 3, 7, 4), (7, 1, 1, 5, 2), (9, 9, 9, 27, 4), (1, 1, 1, 5, 1)])
+def test_generated_grids_engine_log_equals_oracle_log_and_replays(grid, tmp_path):
+    """beyond the four fixtures: ragged grids, one-dof separators, a single-separator tree, the 27-point stencil"""
+    import scipy.io
+    m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch = Cholesky().generate(*grid)
+    ch.write_inputs(m, o, c)
+    ch.analyze(keep_records=True)
+    ch.write_debug_log(str(tmp_path / "engine.log"))
+    d = str(tmp_path / "trace")
+    orc = Oracle(m, o, c)
+    orc.debug_trace(d, str(tmp_path / "oracle.log"), full_precision=True)
+    assert open(str(tmp_path / "engine.log")).read() == open(str(tmp_path / "oracle.log")).read()
+    A = np.asarray(scipy.io.mmread(m).todense())
+    perm = ch.perm()
+    checked, files, worst, mat = replay(np.tril(A[np.ix_(perm, perm)]), str(tmp_path / "oracle.log"), d, rtol=1e-9, atol=1e-11)
+    assert checked == len(files) >= 1
+    assert np.allclose(np.tril(mat), orc.factor_dense(), rtol=1e-9, atol=1e-11)
