@@ -16,6 +16,15 @@ from oracle.oracle import Oracle
 from debug_replay import parse_log, replay
 
 SMALL = ["lapl_9x9", "lapl_25x25", "lapl_400x400"]
+# sha256 of the `-d` log of each fixture, recorded when the oracle's trace of the same fixtures was accepted by
+# the reference's unmodified verify.debug_factor (profiles/debug_trace_r01.md): a change of the log grammar
+# or of the task order has to be deliberate
+LOG_SHA256 = {
+    "lapl_9x9": "73b4a3a16ee5fd7c8e640111425f57cd4401565a52f1d52504a9ff43b7a6ed83",
+    "lapl_25x25": "655b326601348c5bb965e9a0833bdf3bbca00b7ba6f42823a7977369e824e09a",
+    "lapl_400x400": "a8735baf437b6731e30629315e12539a82e5b957566c78e2466c83690fca5c8f",
+    "lapl_3375x3375": "18751c9b1db4f61e1642854bf317a9869637181f4b2586a9d0b842e799bcec69",
+}
 REF = "/root/reference"
 
 
@@ -56,6 +65,8 @@ def test_engine_log_is_the_oracle_log(case, golden, traces, tmp_path):
     ch = Cholesky().load(fx.mtx, fx.ord, fx.clust).analyze(keep_records=True)
     mine = str(tmp_path / "engine.log")
     ch.write_debug_log(mine)
+    import hashlib
+    assert hashlib.sha256(open(mine, "rb").read()).hexdigest() == LOG_SHA256[case]
     blocks, clusters, ops = parse_log(mine)
     assert len(blocks) == fx.struct["blocks"]
     calls = fx.struct["calls"]
