@@ -60,6 +60,8 @@ struct chol {
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  int trsm_batch = 0;       // CHOL_TRSM_BATCH: 1 = experimental trsm_tile<true> (all slab loads in flight at once)
+  int potrf_r = 0;          // CHOL_POTRF_R: 1 / 2 = experimental register-resident right-looking pivot tile (potrf_tile_r / _r2)
   int potrf_w = 1;          // CHOL_POTRF_W: 1 = single-warp column steps (potrf_tile_w), 0 = 64-thread version
   int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
                             // 128^3), 0 = the earlier cp.async kernel
@@ -90,6 +92,8 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
   if (const char *e = getenv("CHOL_GEMM_WS")) c->gemm_ws = atoi(e);
   if (const char *e = getenv("CHOL_POTRF_W")) c->potrf_w = atoi(e);
+  if (const char *e = getenv("CHOL_POTRF_R")) c->potrf_r = atoi(e);
+  if (const char *e = getenv("CHOL_TRSM_BATCH")) c->trsm_batch = atoi(e);
   *out = c;
   return 0;
 }
@@ -297,7 +301,8 @@ static int ensure_device(chol_t *c) {
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
-  CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
+  CK(cudaFuncSetAttribute(trsm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
+  CK(cudaFuncSetAttribute(trsm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
   CK(cudaMalloc((void **)&c->d_flags, kMaxPeers * sizeof(unsigned long long)));
   CK(cudaMemset(c->d_flags, 0, kMaxPeers * sizeof(unsigned long long)));
   c->peers.n = 1, c->peers.rank = 0;
@@ -365,11 +370,14 @@ static void launch_barrier(chol_t *c) {
 static int run_launch(chol_t *c, const Launch &l) {
   switch (l.kind) {
     case K_POTRF:
-      if (c->potrf_w) potrf_tile_w<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      if (c->potrf_r == 2) potrf_tile_r2<<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      else if (c->potrf_r) potrf_tile_r<<<(unsigned)l.count, kPotrfRThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      else if (c->potrf_w) potrf_tile_w<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       else potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
-      trsm_tile<<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      if (c->trsm_batch) trsm_tile<true><<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      else trsm_tile<false><<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
       if (l.count <= 0) break;

@@ -702,12 +702,152 @@ __global__ void __launch_bounds__(kPotrfThreads) potrf_tile_w(const PotrfDesc *_
   }
 }
 
+// potrf_tile_r (EXPERIMENTAL, CHOL_POTRF_R=1; parity-checked on one fixture, 2 % faster only: it spills): the same tile, right-looking and
+// register-resident.  64 threads, thread i holds row i of the tile (64 doubles).  Step k: every thread
+// publishes its entry of column k (unscaled) in shared memory, one barrier, then a_ij -= (a_ik / a_kk) a_jk
+// for the rest of its row and a_ik *= 1/sqrt(a_kk).  One barrier and one rsqrt per column step instead of the
+// blocked dot products of potrf_tile_w (1 140 cycles per column): the step is ~60 dependent cycles of
+// arithmetic plus the barrier.  Entries above the diagonal carry finite garbage that is never stored.
+constexpr int kPotrfRThreads = kNB;
+__device__ __forceinline__ double rsqrt_newton(double s) {
+  // 1/sqrt from the single-precision seed and two Newton steps in double (~2 ulp), as in potrf_tile_w
+  if (s > 1e-30 && s < 1e30) {
+    double r = (double)rsqrtf((float)s);
+    const double hs = 0.5 * s;
+    r = r * (1.5 - hs * r * r);
+    return r * (1.5 - hs * r * r);
+  }
+  return rsqrt(s);
+}
+__global__ void __launch_bounds__(kPotrfRThreads) potrf_tile_r(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+                                                               int *__restrict__ info) {
+  __shared__ __align__(16) double colbuf[2][kNB];
+  const PotrfDesc d = descs[blockIdx.x];
+  double *__restrict__ A = fac + d.off;
+  const int i = threadIdx.x, nb = d.nb;
+  double a[kNB];
+  // rows and columns beyond nb are an identity block: their steps are no-ops
+#pragma unroll
+  for (int c = 0; c < kNB; c++) a[c] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : ((c == i && i >= nb) ? 1.0 : 0.0);
+#pragma unroll
+  for (int k = 0; k < kNB; k++) {
+    double *cb = colbuf[k & 1];  // double-buffered: a thread is at most one step ahead of the slowest one
+    cb[i] = a[k];
+    __syncthreads();
+    double p = cb[k];
+    if (!(p > 0.0)) {
+      if (i == k) atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
+      p = 1.0;
+    }
+    const double r = rsqrt_newton(p);
+    const double t = a[k] * (r * r);
+    a[k] *= r;
+    int j = k + 1;
+    if (j & 1) {
+      if (j < kNB) a[j] -= t * cb[j];
+      j++;
+    }
+#pragma unroll
+    for (; j < kNB; j += 2) {
+      const double2 c2 = *reinterpret_cast<const double2 *>(&cb[j]);
+      a[j] -= t * c2.x;
+      a[j + 1] -= t * c2.y;
+    }
+  }
+  if (i < nb) {
+#pragma unroll
+    for (int c = 0; c < kNB; c++)
+      if (c <= i) A[i + (size_t)c * d.ld] = a[c];
+  }
+}
+
+// potrf_tile_r2 (EXPERIMENTAL, CHOL_POTRF_R=2; parity-checked on one fixture, pivot-tile time of 64^3 5.97 -> 4.90 ms,
+// profiles/experimental_variants_r01.md; off by default until the whole GPU suite has run with it): potrf_tile_r with each row split over
+// two threads (columns 0-31 in warps 0-1, columns 32-63 in warps 2-3): 32 doubles per thread instead of 64,
+// no register spills.  The two halves run different (warp-uniform) code and meet at one named barrier per step.
+__device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__global__ void __launch_bounds__(2 * kNB) potrf_tile_r2(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+                                                         int *__restrict__ info) {
+  __shared__ __align__(16) double colbuf[2][kNB];
+  const PotrfDesc d = descs[blockIdx.x];
+  double *__restrict__ A = fac + d.off;
+  const int i = threadIdx.x & (kNB - 1), h = threadIdx.x >> 6, nb = d.nb;
+  constexpr int H = kNB / 2;
+  double a[H];
+#pragma unroll
+  for (int u = 0; u < H; u++) {
+    const int c = h * H + u;
+    a[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : ((c == i && i >= nb) ? 1.0 : 0.0);
+  }
+  if (h == 0) {
+#pragma unroll
+    for (int k = 0; k < H; k++) {
+      double *cb = colbuf[k & 1];
+      cb[i] = a[k];
+      bar_sync_128();
+      double p = cb[k];
+      if (!(p > 0.0)) {
+        if (i == k) atomicMin(info, d.col0 + k + 1);
+        p = 1.0;
+      }
+      const double r = rsqrt_newton(p);
+      const double t = a[k] * (r * r);
+      a[k] *= r;
+#pragma unroll
+      for (int j = k + 1; j < H; j++) a[j] -= t * cb[j];
+    }
+#pragma unroll
+    for (int k = H; k < kNB; k++) bar_sync_128();  // columns 0-31 are final: keep the barrier count of the other half
+  } else {
+#pragma unroll
+    for (int k = 0; k < H; k++) {
+      const double *cb = colbuf[k & 1];
+      bar_sync_128();
+      double p = cb[k];
+      if (!(p > 0.0)) p = 1.0;  // reported by the thread that owns the pivot
+      const double r = rsqrt_newton(p);
+      const double t = cb[i] * (r * r);
+#pragma unroll
+      for (int u = 0; u < H; u += 2) {
+        const double2 c2 = *reinterpret_cast<const double2 *>(&cb[H + u]);
+        a[u] -= t * c2.x;
+        a[u + 1] -= t * c2.y;
+      }
+    }
+#pragma unroll
+    for (int k = H; k < kNB; k++) {
+      double *cb = colbuf[k & 1];
+      cb[i] = a[k - H];
+      bar_sync_128();
+      double p = cb[k];
+      if (!(p > 0.0)) {
+        if (i == k) atomicMin(info, d.col0 + k + 1);
+        p = 1.0;
+      }
+      const double r = rsqrt_newton(p);
+      const double t = a[k - H] * (r * r);
+      a[k - H] *= r;
+#pragma unroll
+      for (int j = k + 1; j < kNB; j++) a[j - H] -= t * cb[j];
+    }
+  }
+  if (i < nb) {
+#pragma unroll
+    for (int u = 0; u < H; u++)
+      if (h * H + u <= i) A[i + (size_t)(h * H + u) * d.ld] = a[u];
+  }
+}
+
 // 128-row slab per CTA, one row per thread.  The slab (k-major, so a warp reads consecutive words) and
 // L^T live in shared memory; columns are solved eight at a time with eight independent FMA chains, the
 // eight multipliers of one k come as four broadcast vector loads.  Loops are deliberately not fully
 // unrolled: the straight-line version was instruction-fetch bound.
 constexpr int kSlab = 128;
 constexpr int kTrsmSmemBytes = (kNB * kNB + kNB + kNB * kSlab) * 8;
+// BATCH (EXPERIMENTAL, CHOL_TRSM_BATCH=1; parity-checked on one fixture, trsm time of 64^3 4.06 -> 3.47 ms,
+// profiles/experimental_variants_r01.md; off by default until the whole GPU suite has run with it): all 64
+// column loads of the slab row in flight at once instead of eight rounds of eight.
+template <bool BATCH>
 __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
                                                    double *__restrict__ fac) {
   extern __shared__ __align__(16) double tsm[];
@@ -722,12 +862,20 @@ __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ 
   const int row = slab * kSlab + tid;
   const bool live = row < d.rows;
   double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
-  for (int c0 = 0; c0 < nb8; c0 += 8) {
-    double v[8];
+  if (BATCH) {
+    double v[kNB];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = (live && c0 + u < nb) ? Bp[(size_t)(c0 + u) * d.ld] : 0.0;
+    for (int c = 0; c < kNB; c++) v[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
 #pragma unroll
-    for (int u = 0; u < 8; u++) xs[c0 + u][tid] = v[u];
+    for (int c = 0; c < kNB; c++) xs[c][tid] = v[c];
+  } else {
+    for (int c0 = 0; c0 < nb8; c0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (live && c0 + u < nb) ? Bp[(size_t)(c0 + u) * d.ld] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) xs[c0 + u][tid] = v[u];
+    }
   }
   {
     constexpr int PER = kNB * kNB / kSlab;
