@@ -60,8 +60,9 @@ struct chol {
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  int gemm_stages = 3;      // CHOL_GEMM_STAGES: 4 = experimental four-stage operand ring for the 64x64 tiles (not measured yet)
   int trsm_batch = 0;       // CHOL_TRSM_BATCH: 1 = experimental trsm_tile<true> (all slab loads in flight at once)
-  int potrf_r = 0;          // CHOL_POTRF_R: 1 / 2 = experimental register-resident right-looking pivot tile (potrf_tile_r / _r2)
+  int potrf_r = 0;          // CHOL_POTRF_R: 1 / 2 / 3 = experimental register-resident right-looking pivot tile (potrf_tile_r / _r2)
   int potrf_w = 1;          // CHOL_POTRF_W: 1 = single-warp column steps (potrf_tile_w), 0 = 64-thread version
   int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
                             // 128^3), 0 = the earlier cp.async kernel
@@ -94,6 +95,7 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   if (const char *e = getenv("CHOL_POTRF_W")) c->potrf_w = atoi(e);
   if (const char *e = getenv("CHOL_POTRF_R")) c->potrf_r = atoi(e);
   if (const char *e = getenv("CHOL_TRSM_BATCH")) c->trsm_batch = atoi(e);
+  if (const char *e = getenv("CHOL_GEMM_STAGES")) c->gemm_stages = atoi(e);
   *out = c;
   return 0;
 }
@@ -370,7 +372,8 @@ static void launch_barrier(chol_t *c) {
 static int run_launch(chol_t *c, const Launch &l) {
   switch (l.kind) {
     case K_POTRF:
-      if (c->potrf_r == 2) potrf_tile_r2<<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      if (c->potrf_r == 3) potrf_tile_r2<3><<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      else if (c->potrf_r == 2) potrf_tile_r2<1><<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       else if (c->potrf_r) potrf_tile_r<<<(unsigned)l.count, kPotrfRThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       else if (c->potrf_w) potrf_tile_w<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       else potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
@@ -388,6 +391,8 @@ static int run_launch(chol_t *c, const Launch &l) {
         launch_gemm_ws<128, 64, 16, 32, 32, 4, 2>(c, l);
       else if (l.cfg == 1)
         launch_gemm_ws<128, 128, 16, 32, 32, 4, 1>(c, l);
+      else if (c->gemm_ws && c->gemm_stages == 4)  // experimental: four-stage ring (power-of-two indexing), 3 CTAs/SM
+        launch_gemm_ws<64, 64, 16, 32, 32, 4, 3>(c, l);
       else if (c->gemm_ws)
         launch_gemm_ws<64, 64, 16, 32, 32, 3, 4>(c, l);
       else

@@ -766,7 +766,10 @@ __global__ void __launch_bounds__(kPotrfRThreads) potrf_tile_r(const PotrfDesc *
 // two threads (columns 0-31 in warps 0-1, columns 32-63 in warps 2-3): 32 doubles per thread instead of 64,
 // no register spills.  The two halves run different (warp-uniform) code and meet at one named barrier per step.
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-__global__ void __launch_bounds__(2 * kNB) potrf_tile_r2(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+// MINB = 1: 254 registers (the measured build); MINB = 3: 168 registers, no spills, three CTAs per SM for the
+// launches with thousands of tiles at the bottom of the tree (CHOL_POTRF_R=3, not measured yet).
+template <int MINB>
+__global__ void __launch_bounds__(2 * kNB, MINB) potrf_tile_r2(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
                                                          int *__restrict__ info) {
   __shared__ __align__(16) double colbuf[2][kNB];
   const PotrfDesc d = descs[blockIdx.x];
