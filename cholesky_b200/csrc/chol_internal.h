@@ -128,6 +128,7 @@ struct Schedule {
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
   std::vector<int64_t> a_off;
   int nb = 64, nbo = 256, slab = 128;
+  int nbo_small = 0, nbo_small_maxn = 4096;  // experiment: levels whose largest front is <= maxn use this block-column width (0: off)
   int big_m = 192, big_n = 128;  // problems at least this large may use the 128x128 tile configuration ...
   // ... when the launch has at least this many such tiles.  Measured on B200 (128^3): four resident
   // 64x64 CTAs per SM (27.5 TFLOP/s) beat one 128x128 CTA per SM (20.8 with 8 warps, 22.8 with 16),

@@ -261,3 +261,22 @@ def test_level_bytes_add_up_to_the_factor_storage(golden):
     assert leaves["operands"] > 0 and leaves["destinations"] > 0
     with pytest.raises(RuntimeError):
         ch.level_bytes(ch.levels)
+
+
+def test_blocking_knobs_do_not_change_the_executed_work(monkeypatch):
+    """block-column width (global or per level) is a host decision: the launch list changes, the executed GEMM
+    flops, the pivot tiles and the slab count of the factorization do not"""
+    def summary():
+        ch = Cholesky().generate(24, 20, 18, 7, 5).analyze()
+        ls = ch.launches()
+        return (len(ls), round(sum(l["flops"] for l in ls if l["kind"] == "gemm_grouped")),
+                sum(l["ctas"] for l in ls if l["kind"] == "potrf_tile"), ch.flops())
+    base = summary()
+    monkeypatch.setenv("CHOL_NBO", "128")
+    a = summary()
+    monkeypatch.delenv("CHOL_NBO")
+    monkeypatch.setenv("CHOL_NBO_SMALL", "128")
+    monkeypatch.setenv("CHOL_NBO_SMALL_MAXN", "300")
+    b = summary()
+    assert a[1:] == base[1:] and b[1:] == base[1:]
+    assert a[0] >= base[0] and base[0] <= b[0] <= a[0]

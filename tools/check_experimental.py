@@ -14,8 +14,8 @@ sys.path.insert(0, ROOT)
 from cholesky_b200 import Cholesky  # noqa: E402
 
 VARIANTS = [{}, {"CHOL_POTRF_R": "2"}, {"CHOL_POTRF_R": "3"}, {"CHOL_POTRF_R": "1"}, {"CHOL_TRSM_BATCH": "1"}, {"CHOL_POTRF_R": "2", "CHOL_TRSM_BATCH": "1"},
-            {"CHOL_GEMM_STAGES": "4"}]
-KEYS = ("CHOL_POTRF_R", "CHOL_TRSM_BATCH", "CHOL_GEMM_STAGES")
+            {"CHOL_GEMM_STAGES": "4"}, {"CHOL_NBO_SMALL": "128"}]
+KEYS = ("CHOL_POTRF_R", "CHOL_TRSM_BATCH", "CHOL_GEMM_STAGES", "CHOL_NBO_SMALL")
 
 
 def main():
