@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -168,6 +169,12 @@ int write_debug_log(const Problem &P, const Symbolic &S, FILE *f, std::string &e
 // binary block dump of the factor (factor_file.cc); the converter back to text is chol_factor_binary_to_mtx
 int write_factor_binary(const Problem &P, const Symbolic &S, const double *fac, int rank, int world, int depth, const char *path,
                         std::string &err);
+
+// host-side parallel loop over [0, n) in contiguous chunks, one per worker (CHOL_HOST_THREADS, default: hardware
+// concurrency capped at 16); fn(begin, end, worker).  Used where every item is independent and the result does
+// not depend on the split (assembly map, interval-0 flags, Filled-record evidence).
+void parallel_chunks(int64_t n, const std::function<void(int64_t, int64_t, int)> &fn, int *workers_out = nullptr);
+int host_threads();
 
 uint64_t mix64(uint64_t x);
 uint64_t filled_hash(const FilledRec &r);

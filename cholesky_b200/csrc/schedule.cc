@@ -257,19 +257,27 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     for (int h = 1; h <= N; h++)
       for (int i = 0; i < P.sz[h]; i++) rowheap[P.start[h] + i] = h;
     D.a_off.assign((size_t)P.nz, -1);
-    for (int64_t e = 0; e < P.nz; e++) {
-      if (P.ev[e] == 0.0) continue;
-      int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
-      if (pi < pj) std::swap(pi, pj);
-      int hr = rowheap[pi], hc = rowheap[pj];
-      int d = P.level_of(hc) - P.level_of(hr);
-      if (d < 0 || (hc >> d) != hr) continue;
-      int own = owner_of(hc);
-      if (world > 1 && !(own == rank || (own < 0 && rank == 0))) continue;
-      int r = locate(hc, pi);
-      if (r < 0) return err = "internal: nonzero outside the filled pattern", -1;
-      D.a_off[e] = S.poff[hc] + r + (int64_t)(pj - P.start[hc]) * S.ld[hc];
-    }
+    std::vector<int> bad(64, 0);
+    parallel_chunks(P.nz, [&](int64_t e0, int64_t e1, int w) {  // every entry is independent
+      for (int64_t e = e0; e < e1; e++) {
+        if (P.ev[e] == 0.0) continue;
+        int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
+        if (pi < pj) std::swap(pi, pj);
+        int hr = rowheap[pi], hc = rowheap[pj];
+        int d = P.level_of(hc) - P.level_of(hr);
+        if (d < 0 || (hc >> d) != hr) continue;
+        int own = owner_of(hc);
+        if (world > 1 && !(own == rank || (own < 0 && rank == 0))) continue;
+        int r = locate(hc, pi);
+        if (r < 0) {
+          bad[w] = 1;
+          return;
+        }
+        D.a_off[e] = S.poff[hc] + r + (int64_t)(pj - P.start[hc]) * S.ld[hc];
+      }
+    });
+    for (int b : bad)
+      if (b) return err = "internal: nonzero outside the filled pattern", -1;
   }
 
   std::vector<Pair> pairs;

@@ -6,7 +6,9 @@
 // The `Filled` records the reference would hold at every interval label are counted and hashed
 // on the fly (and kept on request) so the pattern can be compared bit for bit with the oracle.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "chol_internal.h"
 
@@ -28,6 +30,26 @@ uint64_t filled_hash(const FilledRec &r) {
 namespace {
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 }  // namespace
+
+int host_threads() {
+  static int n = [] {
+    int v = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("CHOL_HOST_THREADS")) v = atoi(e);
+    return std::max(1, std::min(v, 16));
+  }();
+  return n;
+}
+void parallel_chunks(int64_t n, const std::function<void(int64_t, int64_t, int)> &fn, int *workers_out) {
+  const int w = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), n / 4096));
+  if (workers_out) *workers_out = w;
+  if (w == 1) {
+    fn(0, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < w; t++) th.emplace_back([&, t] { fn(n * t / w, n * (t + 1) / w, t); });
+  for (auto &x : th) x.join();
+}
 
 int analyze(const Problem &P, Symbolic &S, bool keep, std::string &err) {
   const int L = P.levels, N = P.N;
@@ -82,17 +104,40 @@ int analyze(const Problem &P, Symbolic &S, bool keep, std::string &err) {
       const auto &b = S.cb[h][0];
       return (int)(std::upper_bound(b.begin(), b.end(), pos) - b.begin()) - 1;
     };
+    // pass 1 (parallel): block and interval-0 cluster of every entry; pass 2 (serial): set the flags, allocating
+    // a block's bitmap on first touch
+    std::vector<int64_t> eb((size_t)P.nz, -1);
+    std::vector<int32_t> ez((size_t)P.nz, 0);
+    std::vector<int> bad(64, 0);
+    parallel_chunks(P.nz, [&](int64_t e0, int64_t e1, int w) {
+      for (int64_t e = e0; e < e1; e++) {
+        if (P.ev[e] == 0.0) continue;
+        if (P.ei[e] < 0 || P.ei[e] >= P.n || P.ej[e] < 0 || P.ej[e] >= P.n) {
+          bad[w] = 1;
+          return;
+        }
+        int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
+        if (pi < pj) std::swap(pi, pj);
+        int hr = rowheap[pi], hc = rowheap[pj];
+        int d = lev[hc] - lev[hr];
+        if (d < 0 || (hc >> d) != hr) continue;  // couples two unrelated separators: no block, dropped (mmat.rg:1191)
+        eb[e] = blk(hr, hc);
+        ez[e] = cluster0(hr, pi - P.start[hr]) * nc(hc, 0) + cluster0(hc, pj - P.start[hc]);
+      }
+    });
+    for (int b : bad)
+      if (b) return err = "matrix entry out of range", -1;
+    std::vector<int> rows0(N + 2), cols0(N + 2);
     for (int64_t e = 0; e < P.nz; e++) {
-      if (P.ev[e] == 0.0) continue;
-      if (P.ei[e] < 0 || P.ei[e] >= P.n || P.ej[e] < 0 || P.ej[e] >= P.n) return err = "matrix entry out of range", -1;
-      int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
-      if (pi < pj) std::swap(pi, pj);
-      int hr = rowheap[pi], hc = rowheap[pj];
-      int d = lev[hc] - lev[hr];
-      if (d < 0 || (hc >> d) != hr) continue;  // couples two unrelated separators: no block, dropped (mmat.rg:1191)
-      auto &f = flag[blk(hr, hc)];
-      if (f.empty()) f.assign((size_t)nc(hr, 0) * nc(hc, 0), 0);
-      f[(size_t)cluster0(hr, pi - P.start[hr]) * nc(hc, 0) + cluster0(hc, pj - P.start[hc])] = 1;
+      if (eb[e] < 0) continue;
+      auto &f = flag[eb[e]];
+      if (f.empty()) {
+        // the block id encodes (hr, hc): hc owns the ids boff[hc] .. boff[hc] + lev[hc]
+        int hc = (int)(std::upper_bound(boff.begin() + 1, boff.begin() + N + 1, eb[e]) - boff.begin()) - 1;
+        int hr = hc >> (int)(eb[e] - boff[hc]);
+        f.assign((size_t)nc(hr, 0) * nc(hc, 0), 0);
+      }
+      f[(size_t)ez[e]] = 1;
     }
   }
 
@@ -162,24 +207,37 @@ int analyze(const Problem &P, Symbolic &S, bool keep, std::string &err) {
         }
       }
     }
-    // ---- snapshot F[t] (mmat.rg:1000-1016): every flagged cluster of every block that still carries flags
-    for (int hc = 1; hc <= N; hc++)
-      for (int hr = hc; hr >= 1; hr >>= 1) {
-        const auto &f = flag[blk(hr, hc)];
-        if (f.empty()) continue;
-        int ncc = nc(hc, k);
-        for (size_t z = 0; z < f.size(); z++)
-          if (f[z]) {
-            int rc = (int)(z / ncc), cc = (int)(z % ncc);
-            FilledRec r;
-            r.filled = 0, r.sep_x = P.label_of(hr), r.sep_y = P.label_of(hc), r.interval = t, r.cluster = (int64_t)z;
-            r.lo_x = P.start[hr] + S.cb[hr][k][rc], r.hi_x = P.start[hr] + S.cb[hr][k][rc + 1] - 1;
-            r.lo_y = P.start[hc] + S.cb[hc][k][cc], r.hi_y = P.start[hc] + S.cb[hc][k][cc + 1] - 1;
-            S.nfilled[t]++;
-            S.checksum[t] += filled_hash(r);
-            if (keep) S.records[t].push_back(r);
+    // ---- snapshot F[t] (mmat.rg:1000-1016): every flagged cluster of every block that still carries flags.
+    // Count and checksum are order independent, so column separators are spread over the host threads.
+    {
+      std::vector<int64_t> cnt(64, 0);
+      std::vector<uint64_t> sum(64, 0);
+      std::vector<std::vector<FilledRec>> recs(64);
+      parallel_chunks(N, [&](int64_t h0, int64_t h1, int w) {
+        for (int hc = (int)h0 + 1; hc <= (int)h1; hc++)
+          for (int hr = hc; hr >= 1; hr >>= 1) {
+            const auto &f = flag[blk(hr, hc)];
+            if (f.empty()) continue;
+            int ncc = nc(hc, k);
+            for (size_t z = 0; z < f.size(); z++)
+              if (f[z]) {
+                int rc = (int)(z / ncc), cc = (int)(z % ncc);
+                FilledRec r;
+                r.filled = 0, r.sep_x = P.label_of(hr), r.sep_y = P.label_of(hc), r.interval = t, r.cluster = (int64_t)z;
+                r.lo_x = P.start[hr] + S.cb[hr][k][rc], r.hi_x = P.start[hr] + S.cb[hr][k][rc + 1] - 1;
+                r.lo_y = P.start[hc] + S.cb[hc][k][cc], r.hi_y = P.start[hc] + S.cb[hc][k][cc + 1] - 1;
+                cnt[w]++;
+                sum[w] += filled_hash(r);
+                if (keep) recs[w].push_back(r);
+              }
           }
+      });
+      for (int w = 0; w < 64; w++) {
+        S.nfilled[t] += cnt[w];
+        S.checksum[t] += sum[w];
+        if (keep) S.records[t].insert(S.records[t].end(), recs[w].begin(), recs[w].end());
       }
+    }
     if (keep)
       std::sort(S.records[t].begin(), S.records[t].end(), [](const FilledRec &a, const FilledRec &b) {
         if (a.sep_x != b.sep_x) return a.sep_x < b.sep_x;
