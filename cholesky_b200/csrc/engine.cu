@@ -60,6 +60,12 @@ struct chol {
   unsigned long long *d_flags = nullptr;
   unsigned long long epoch = 0;
   bool peers_ready = false;
+  // CHOL_GRAPH=1 (experimental, not measured yet): the whole level loop of a single-GPU handle is captured once
+  // into a CUDA graph (both streams and their events) and replayed; for the launch-bound workloads (512^2: 400
+  // launches in 3 ms).  graph_runs counts the eager runs since the schedule was uploaded: the first one stays
+  // eager (one-time function attributes), the second is captured.
+  int use_graph = 0, graph_runs = 0;
+  cudaGraphExec_t graph_exec = nullptr;
   int gemm_stages = 3;      // CHOL_GEMM_STAGES: 4 = experimental four-stage operand ring for the 64x64 tiles (not measured yet)
   int trsm_batch = 0;       // CHOL_TRSM_BATCH: 1 = experimental trsm_tile<true> (all slab loads in flight at once)
   int potrf_r = 0;          // CHOL_POTRF_R: 1 / 2 / 3 = experimental register-resident right-looking pivot tile (potrf_tile_r / _r2)
@@ -96,13 +102,16 @@ int chol_create(const int *devices, int ngpu, chol_t **out) {
   if (const char *e = getenv("CHOL_POTRF_R")) c->potrf_r = atoi(e);
   if (const char *e = getenv("CHOL_TRSM_BATCH")) c->trsm_batch = atoi(e);
   if (const char *e = getenv("CHOL_GEMM_STAGES")) c->gemm_stages = atoi(e);
+  if (const char *e = getenv("CHOL_GRAPH")) c->use_graph = atoi(e);
   *out = c;
   return 0;
 }
 
 static void free_solve(chol_t *c);
+static void drop_graph(chol_t *c);
 static void free_device(chol_t *c) {
   if (!c->device_ready) return;
+  drop_graph(c);
   free_solve(c);
   cudaSetDevice(c->device);
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
@@ -255,7 +264,12 @@ static int upload(chol_t *c, T **dst, const std::vector<T> &src) {
 }
 
 extern "C" {
+static void drop_graph(chol_t *c) {
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr, c->graph_runs = 0;
+}
 static int upload_schedule(chol_t *c) {
+  drop_graph(c);  // the captured launches point into the descriptor arrays replaced below
   cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles);
   c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_potrf = nullptr, c->d_trsm = nullptr, c->d_trsm_tiles = nullptr;
   if (upload(c, &c->d_probs, c->D.probs)) return -100;
@@ -423,6 +437,16 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->evs.push_back(e);
   }
+  // graph replay / capture: whole level loop, single GPU, uninstrumented (see chol::use_graph)
+  const bool whole = lvl_from >= c->P.levels - 1 && lvl_to <= 0 && phase_mask == 7;
+  const bool graphable = c->use_graph && c->world == 1 && whole && !per_kernel_timing;
+  if (graphable && c->graph_exec) {
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    return 0;
+  }
+  const bool capture = graphable && c->graph_runs >= 1;
+  if (graphable) c->graph_runs++;
+  if (capture) CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   if (c->D.lookahead) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->stream1, c->ev_fork, 0));
@@ -448,6 +472,19 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   if (c->D.lookahead) {  // partial runs (piecewise calls) may leave work on the chain stream: join it
     CK(cudaEventRecord(c->ev_join, c->stream1));
     CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  }
+  if (capture) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture(c->stream, &g));
+    cudaError_t e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      c->graph_exec = nullptr;
+      c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);
+      return -100;
+    }
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));  // the captured launches have not run yet
+    return 0;
   }
   CK(cudaGetLastError());
   if (per_kernel_timing) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Parity + timing of the experimental kernel variants (default off) in one process, a few seconds of GPU:
-for every variant, factor the 15^3 fixture and compare with the golden factor, then time 64^3.
+for every variant, factor the 15^3 fixture and compare with the golden factor, then time 64^3 and 512^2.
   python tools/check_experimental.py            (needs a GPU)"""
 import json
 import os
@@ -14,8 +14,9 @@ sys.path.insert(0, ROOT)
 from cholesky_b200 import Cholesky  # noqa: E402
 
 VARIANTS = [{}, {"CHOL_POTRF_R": "2"}, {"CHOL_POTRF_R": "3"}, {"CHOL_POTRF_R": "1"}, {"CHOL_TRSM_BATCH": "1"}, {"CHOL_POTRF_R": "2", "CHOL_TRSM_BATCH": "1"},
-            {"CHOL_GEMM_STAGES": "4"}, {"CHOL_NBO_SMALL": "128"}]
-KEYS = ("CHOL_POTRF_R", "CHOL_TRSM_BATCH", "CHOL_GEMM_STAGES", "CHOL_NBO_SMALL")
+            {"CHOL_GEMM_STAGES": "4"}, {"CHOL_NBO_SMALL": "128"}, {"CHOL_GRAPH": "1"},
+            {"CHOL_GRAPH": "1", "CHOL_POTRF_R": "2", "CHOL_TRSM_BATCH": "1"}]
+KEYS = ("CHOL_POTRF_R", "CHOL_TRSM_BATCH", "CHOL_GEMM_STAGES", "CHOL_NBO_SMALL", "CHOL_GRAPH")
 
 
 def main():
@@ -46,6 +47,9 @@ def main():
             out["ms_64"] = st.seconds_best * 1e3
             out.update({k: round(x, 3) for k, x in big.kernel_times().items() if k.endswith("_ms")})
             big.close()
+            flat = Cholesky().generate(512, 512, 1, 5, 0).analyze()   # the launch-bound BASELINE config 2
+            out["ms_512sq"] = flat.factor(iterations=5, warmup=2).seconds_best * 1e3
+            flat.close()
         except Exception as e:  # noqa: BLE001
             out["error"] = str(e)
         print(json.dumps(out), flush=True)
