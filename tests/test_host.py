@@ -280,3 +280,32 @@ def test_blocking_knobs_do_not_change_the_executed_work(monkeypatch):
     b = summary()
     assert a[1:] == base[1:] and b[1:] == base[1:]
     assert a[0] >= base[0] and base[0] <= b[0] <= a[0]
+
+
+@pytest.mark.parametrize("grid", [(512, 512, 1, 5, 0), (64, 64, 64, 7, 0), (128, 128, 128, 7, 0), (96, 96, 96, 27, 0)],
+                         ids=["config2_512sq", "config3_64cubed", "config4_128cubed", "config5_96cubed_27pt"])
+def test_block_pattern_is_bit_exact_at_the_baseline_sizes(grid, tmp_path):
+    """BASELINE.json configs 2-5 at full size: the engine's symbolic phase against the oracle's restatement of
+    compute_filled_clusters -- every `Filled` record of every interval label (count + order-independent
+    checksum of all nine fields), the permutation, the reference's BLAS call counts and its flop total"""
+    import shutil
+    from oracle import oracle as orc
+    d = str(tmp_path / "inputs")
+    os.makedirs(d)
+    m, o, c = (os.path.join(d, x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch = Cholesky().generate(*grid)
+    ch.write_inputs(m, o, c)
+    ch.analyze()
+    oc = orc.Oracle(m, o, c)
+    try:
+        assert ch.levels == oc.levels and ch.num_separators == oc.num_separators
+        np.testing.assert_array_equal(ch.perm(), oc.perm())
+        for t in range(ch.levels):
+            assert ch.num_filled(t) == oc.num_filled(t), t
+            assert ch.filled_checksum(t) == oc.filled_checksum(t), t
+        assert ch.call_counts() == oc.call_counts()
+        assert ch.flops() == oc.flops()
+        assert ch.num_blocks() == oc.num_blocks() and ch.num_clusters0() == oc.num_clusters0()
+    finally:
+        oc.close()
+        shutil.rmtree(d)
