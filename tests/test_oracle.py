@@ -136,3 +136,27 @@ def test_mmio_ref_banner_if_built(golden):
         libc.fclose(f)
         assert tc.raw == b"MCRH"
         assert (M.value, N.value, nz.value) == (g.n, g.n, g.struct["nz"])
+
+
+@pytest.mark.parametrize("grid", [(12, 12, 12, 27, 0), (11, 9, 7, 7, 4), (40, 33, 1, 5, 0)])
+def test_oracle_on_generated_grids_matches_dense_cholesky(grid, tmp_path):
+    """beyond the fixtures: the generated inputs of the BASELINE stencils (27-point is this repo's definition,
+    SURVEY 8(d)) through the oracle against SciPy's dense factor of the permuted matrix, and the solve"""
+    import scipy.io
+    import scipy.linalg
+    from cholesky_b200 import Cholesky
+    m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch = Cholesky().generate(*grid)
+    ch.write_inputs(m, o, c)
+    orc_ = orc.Oracle(m, o, c)
+    orc_.factor(threads=1)
+    A = np.asarray(scipy.io.mmread(m).todense())
+    perm = orc_.perm()
+    Lref = scipy.linalg.cholesky(A[np.ix_(perm, perm)], lower=True)
+    L = orc_.factor_dense()
+    scale = np.maximum(np.abs(Lref), 1e-6 * np.abs(Lref).max())
+    assert np.max(np.abs(L - Lref) / scale) <= 1e-11
+    assert np.count_nonzero(L) == orc_.factor_nnz()
+    b = np.random.default_rng(0).integers(1, 11, size=A.shape[0]).astype(np.float64)
+    x = orc_.solve(b)
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1e-12
