@@ -8,15 +8,15 @@ LIB_PATH = os.path.join(HERE, "libcholesky_b200.so")
 
 # every symbol include/cholesky.h, include/chol_mmio.h and include/chol_mnd.h declare
 EXPORTS = [
-    "chol_create", "chol_destroy", "chol_last_error", "register_mappers", "chol_load", "chol_load_arrays",
+    "chol_create", "chol_num_ranks", "chol_rank_handle", "chol_destroy", "chol_last_error", "register_mappers", "chol_load", "chol_load_arrays",
     "chol_generate", "chol_write_inputs", "chol_analyze", "chol_n", "chol_nz", "chol_levels",
     "chol_num_separators", "chol_max_int_size", "chol_num_blocks", "chol_num_clusters0", "chol_get_perm",
     "chol_get_sep_sizes", "chol_get_block_bounds", "chol_num_filled", "chol_get_filled", "chol_filled_checksum",
     "chol_flops", "chol_flops_by_level", "chol_call_counts", "chol_factor_doubles", "chol_level_bytes", "chol_assemble", "chol_factor",
     "chol_fused_dpotrf", "chol_fused_dtrsm", "chol_fused_update", "chol_factor_host", "chol_synchronize",
     "chol_kernel_times", "chol_launch_times", "chol_num_launches", "chol_get_launch", "chol_set_partition", "chol_ipc_export",
-    "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor", "chol_write_factor_binary", "chol_factor_binary_to_mtx",
-    "chol_residual", "chol_write_debug_log", "chol_factor_debug", "chol_solve", "chol_solve_top_size", "chol_solve_forward", "chol_solve_backward", "chol_solve_stats", "chol_matvec", "chol_read_vector", "chol_write_solution",
+    "chol_ipc_import", "chol_partition_stats", "chol_rank", "chol_world", "chol_top_copies_diff", "chol_factor_nnz", "chol_get_factor_coo", "chol_get_factor_dense", "chol_write_factor", "chol_write_factor_binary", "chol_factor_binary_to_mtx",
+    "chol_residual", "chol_residual_partial", "chol_residual_finish", "chol_write_debug_log", "chol_factor_debug", "chol_solve", "chol_solve_top_size", "chol_solve_forward", "chol_solve_backward", "chol_solve_stats", "chol_matvec", "chol_read_vector", "chol_write_solution",
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_write_banner", "mm_write_mtx_crd_size", "mm_typecode_to_str",
     "mnd_read_separators", "mnd_read_clusters", "mnd_read_matrix", "mnd_read_vector", "mnd_hash_sax",
 ]
@@ -41,6 +41,7 @@ def load():
             "(make -C cholesky_b200/csrc). The engine has no fallback path.")
     L = C.CDLL(LIB_PATH)
     L.chol_last_error.restype = C.c_char_p
+    L.chol_rank_handle.restype = C.c_void_p
     L.chol_flops.restype = C.c_double
     L.chol_filled_checksum.restype = C.c_uint64
     L.mnd_hash_sax.restype = C.c_uint64

@@ -104,20 +104,37 @@ struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
   int ld, nb, rows, pad;
 };
 
-enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_BARRIER = 3, K_ALLREDUCE = 4, K_NOP = 5 };
+// One rectangle of a top panel: rows [r0, r0 + rows) x cols [c0, c0 + cols), first entry at factor offset `off`.
+// K_PUSH copies it into the peers' copies of the factor (NVLink peer stores); K_REDUCE sums the peers' partial
+// sums of it into this rank's copy (peer loads); `tri0` >= 0: rows and columns are the pivot block's, entries
+// with column > tri0 + row (strictly above the diagonal) are skipped.
+struct RectDesc {
+  int64_t off;
+  int ld, rows, cols, tri0;
+};
+
+enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_SYNC = 3, K_REDUCE = 4, K_NOP = 5, K_PUSH = 6, K_PANEL = 7 };
 enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
+enum FlagSlot { SLOT_WORLD = 0, SLOT_GROUP = 1, SLOT_DIAG = 2, kFlagSlots = 4 };
 struct Launch {
   int kind;
   int level;
   int phase;
-  int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[]
+  int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[] / rects[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
-  int cfg;               // GEMM tile configuration: 0 = 64x64 CTA tiles, 1 = 128x128, 2 = 128x64
-  int shared;            // multi-GPU: 1 = this rank's tiles are stored into every rank's copy, 2 = owned tiles, local store
-  int stream;            // 0 = update stream, 1 = chain stream (look-ahead)
+  int cfg;               // GEMM: 0 = 64x64 CTA tiles on shared-memory operand rings, 3 = one warp per 32x32 tile
+  int stream;            // 0 = update stream, 1 = chain stream (look-ahead), 2 = background pushes
   int wait_ev, rec_ev;   // event to wait for before / to record after the launch (-1: none)
+  // multi-GPU (K_PUSH / K_SYNC / K_REDUCE): `mask` = ranks the rectangles are pushed to / reduced from;
+  // after a push (or as the first half of a sync) flag word (slot, this rank) of every rank in `sig_mask`
+  // is raised to `seq`; a sync then waits until its own words (slot, r) have reached `seq` for every r in
+  // `wait_mask`.  seq values grow in program order on every (slot, source) pair.
+  unsigned mask, sig_mask, wait_mask;
+  int slot;
+  int64_t seq;
 };
 
+constexpr int kRowBlock = 256;  // default and largest row block (CHOL_ROW_BLOCK: 64 / 128 / 256, so that tests deal small panels too)
 struct Schedule {
   std::vector<GemmProblem> probs;
   std::vector<GemmContrib> contribs;
@@ -125,17 +142,11 @@ struct Schedule {
   std::vector<PotrfDesc> potrf;
   std::vector<TrsmDesc> trsm;
   std::vector<TileRef> trsm_tiles;  // prob = index into trsm[], tr = slab index
+  std::vector<RectDesc> rects;      // rectangles of K_PUSH / K_REDUCE launches
   std::vector<Launch> launches;
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
   std::vector<int64_t> a_off;
   int nb = 64, nbo = 256, slab = 128;
-  int nbo_small = 0, nbo_small_maxn = 4096;  // experiment: levels whose largest front is <= maxn use this block-column width (0: off)
-  int big_m = 192, big_n = 128;  // problems at least this large may use the 128x128 tile configuration ...
-  // ... when the launch has at least this many such tiles.  Measured on B200 (128^3): four resident
-  // 64x64 CTAs per SM (27.5 TFLOP/s) beat one 128x128 CTA per SM (20.8 with 8 warps, 22.8 with 16),
-  // so the large configuration is off by default (CHOL_MIN_TILES_128 re-enables it for experiments).
-  int min_tiles_128 = 1 << 30;
-  int big_cfg = 1;  // tile configuration of big problems: 1 = 128x128, 2 = 128x64
   // small fronts: Schur problems with M, N <= small_mn and total K <= small_k run as one warp per 32x32
   // tile (cfg 3, gemm_small_warp): no shared memory, no barriers (CHOL_SMALL_FRONT=0: off)
   bool small_front = true;
@@ -145,9 +156,29 @@ struct Schedule {
   bool split_phases = false;  // true: fused_dpotrf and fused_dtrsm as separate launch sequences (piecewise API)
   bool lookahead = true;      // chain kernels on a second stream, overlapping the trailing updates (CHOL_LOOKAHEAD=0: off)
   int num_events = 0;         // cross-stream events the launch list refers to
-  int64_t top_doubles = 0;         // leading part of the factor buffer that holds the shared top panels
-  double shared_min_flops = 2e9;   // top-level GEMM launches at least this large are split across ranks
+  int64_t top_doubles = 0;    // leading part of the factor buffer that holds the top panels (one copy per rank)
+  int row_block = kRowBlock;  // rows of a top panel are dealt to its group in blocks of this many (= block-column width there)
 };
+
+// Ownership of the rows of a top panel (multi-GPU): separator h on tree level lv < depth belongs to the
+// 2^(depth - lv) ranks whose subtrees hang under it; its stored rows are dealt to them in blocks of 256,
+// boustrophedon (0 1 .. G-1 G-1 .. 1 0), which balances both the triangular Schur updates and the shrinking
+// trailing matrix.
+struct TopGroup {
+  int base, size, rb;
+  unsigned mask() const { return ((1u << size) - 1u) << base; }
+  int owner(int block) const {
+    const int m = block % (2 * size);
+    return base + (m < size ? m : 2 * size - 1 - m);
+  }
+};
+inline TopGroup top_group(int h, int lv, int depth, int rb) {
+  TopGroup g;
+  g.rb = rb;
+  g.size = 1 << (depth - lv);
+  g.base = (h << (depth - lv)) - (1 << depth);
+  return g;
+}
 
 // only_heap != 0: the launches of that one separator alone (no assembly map) -- the stepwise debug trace
 int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, int world, bool split_phases, std::string &err,

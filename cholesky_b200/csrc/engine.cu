@@ -1,5 +1,12 @@
 // C ABI of the engine (include/cholesky.h): handle, loaders, host symbolic analysis, GPU numeric
 // factorization driven by the compiled level schedule, result access.
+//
+// A handle drives one GPU, or -- chol_create(devices, ngpu > 1) -- a group of GPUs from one process: the
+// parent handle keeps the problem and the symbolic structure, one rank handle per device keeps that
+// rank's schedule, buffers and streams, and every device-side call fans out over one host thread per
+// rank (the ranks meet in flag words in peer memory, so their launch lists must be issued concurrently).
+// The one-process-per-GPU form (chol_set_partition + chol_ipc_*) runs the same rank code with the peers'
+// buffers mapped through CUDA IPC instead.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -7,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/chol_mmio.h"
@@ -16,22 +24,31 @@
 #include "kernels.cuh"
 #include "solve.h"
 #include "solve_kernels.cuh"
+#include "verify_kernels.cuh"
 
 using namespace chb;
 
 constexpr int kMaxDevices = 16;
-
+constexpr int kStreams = 3;  // update stream, chain stream (look-ahead), background pushes
 
 struct SolveDev;
+struct ResDev;
 struct chol {
   std::string err;
+  Problem own_P;
+  Symbolic own_S;
+  Problem &P;   // a rank handle of an in-process group refers to its parent's
+  Symbolic &S;
+  chol *parent = nullptr;
+  std::vector<chol *> sub;  // in-process multi-GPU: one rank handle per device (empty otherwise)
   SolveDev *solve = nullptr;  // solve schedule and buffers, built on first use
+  ResDev *res = nullptr;      // residual-check descriptors, built on first use
   int device = 0;
-  Problem P;
-  Symbolic S;
   Schedule D;
-  bool loaded = false, analyzed = false, device_ready = false, assembled = false;
-  cudaStream_t stream = nullptr;
+  bool loaded = false, analyzed = false, device_ready = false, assembled = false, factored = false;
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  cudaStream_t &stream = streams[0];
+  cudaStream_t cur = nullptr;  // stream of the launch being issued
   double *d_fac = nullptr;
   double *d_vals = nullptr;
   int64_t *d_aoff = nullptr;
@@ -41,39 +58,40 @@ struct chol {
   PotrfDesc *d_potrf = nullptr;
   TrsmDesc *d_trsm = nullptr;
   TileRef *d_trsm_tiles = nullptr;
-  int *d_info = nullptr;
+  RectDesc *d_rects = nullptr;
+  int *d_info = nullptr;  // [0] first non-positive pivot (1-based permuted column), [1] a peer wait timed out
   int64_t *d_diag_off = nullptr;
   double *d_diag = nullptr;
   double *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
   std::vector<double> h_fac;  // host copy of the factor, fetched lazily
   bool h_fac_valid = false;
-  cudaStream_t stream1 = nullptr, cur = nullptr;  // chain stream (look-ahead); stream of the launch being issued
-  std::vector<cudaEvent_t> evs;                   // cross-stream events of the launch list
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  double k_ms[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<cudaEvent_t> evs;  // cross-stream events of the launch list
+  cudaEvent_t ev_fork = nullptr, ev_join[kStreams] = {nullptr, nullptr, nullptr};
+  double k_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double k_gemm_flops = 0;
   std::vector<float> launch_ms;  // per launch, from the last instrumented pass
-  // multi-GPU: one handle per rank; peers' factor buffers and flag words mapped through CUDA IPC
+  // multi-GPU: flag words in peer memory, peers' buffers (IPC or in-process peer access)
   int rank = 0, world = 1;
   Peers peers = {};
   unsigned long long *d_flags = nullptr;
-  unsigned long long epoch = 0;
+  unsigned *d_counters = nullptr;
+  unsigned long long run_id = 0;  // whole-factorization runs so far: the high half of every flag value
   bool peers_ready = false;
-  // CHOL_GRAPH=1 (experimental, not measured yet): the whole level loop of a single-GPU handle is captured once
-  // into a CUDA graph (both streams and their events) and replayed; for the launch-bound workloads (512^2: 400
-  // launches in 3 ms).  graph_runs counts the eager runs since the schedule was uploaded: the first one stays
-  // eager (one-time function attributes), the second is captured.
-  int use_graph = 0, graph_runs = 0;
+  int num_sms = 148;
+  // CUDA-graph replay of the level loop (the analogue of the reference's __demand(__trace), mmat.rg:1211): the
+  // launch list of a single-GPU handle, both streams and their events, is captured once and replayed.  Pays
+  // only where the step is launch-bound (512^2: 2.64 -> 2.50 ms; 128^3: 933 -> 948 ms, measured), so by
+  // default (CHOL_GRAPH unset) it is used when the factorization has less than kGraphFlops flops.
+  // graph_runs counts the eager runs since the schedule was uploaded: the first one stays eager (one-time
+  // function attributes), the second is captured.
+  int use_graph = -1, graph_runs = 0;
   cudaGraphExec_t graph_exec = nullptr;
-  int gemm_stages = 3;      // CHOL_GEMM_STAGES: 4 = experimental four-stage operand ring for the 64x64 tiles (not measured yet)
-  int trsm_batch = 0;       // CHOL_TRSM_BATCH: 1 = experimental trsm_tile<true> (all slab loads in flight at once)
-  int potrf_r = 0;          // CHOL_POTRF_R: 1 / 2 / 3 = experimental register-resident right-looking pivot tile (potrf_tile_r / _r2)
-  int potrf_w = 1;          // CHOL_POTRF_W: 1 = single-warp column steps (potrf_tile_w), 0 = 64-thread version
-  int gemm_ws = 1;          // CHOL_GEMM_WS: 1 = warp-specialised TMA bulk-copy kernel (default, 8% faster on
-                            // 128^3), 0 = the earlier cp.async kernel
   std::vector<void *> ipc_opened;
+  chol() : P(own_P), S(own_S) {}
+  explicit chol(chol *par) : P(par->P), S(par->S), parent(par) {}
 };
+constexpr double kGraphFlops = 2e10;
 
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -89,60 +107,111 @@ static int fail(chol_t *c, const std::string &m) {
   return -1;
 }
 
+// fn(rank handle) on every rank of the handle, one host thread per rank for a group
+template <typename F>
+static int for_ranks(chol_t *c, F fn) {
+  if (c->sub.empty()) {
+    cudaSetDevice(c->device);
+    return fn(c);
+  }
+  std::vector<int> rc(c->sub.size(), 0);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < c->sub.size(); i++)
+    th.emplace_back([&, i] {
+      cudaSetDevice(c->sub[i]->device);
+      rc[i] = fn(c->sub[i]);
+    });
+  for (auto &t : th) t.join();
+  for (size_t i = 0; i < rc.size(); i++)
+    if (rc[i]) {
+      c->err = "rank " + std::to_string(i) + ": " + c->sub[i]->err;
+      return rc[i];
+    }
+  return 0;
+}
+static bool is_group(const chol_t *c) { return !c->sub.empty(); }
+
 extern "C" {
 
 void register_mappers(void) {}
 
 int chol_create(const int *devices, int ngpu, chol_t **out) {
   if (!out) return -1;
+  *out = nullptr;
+  if (ngpu < 0 || ngpu > kMaxPeers || (ngpu > 1 && (ngpu & (ngpu - 1)))) return -1;  // 1, 2, 4 or 8 GPUs
   chol_t *c = new chol();
   c->device = (devices && ngpu > 0) ? devices[0] : 0;
-  if (const char *e = getenv("CHOL_GEMM_WS")) c->gemm_ws = atoi(e);
-  if (const char *e = getenv("CHOL_POTRF_W")) c->potrf_w = atoi(e);
-  if (const char *e = getenv("CHOL_POTRF_R")) c->potrf_r = atoi(e);
-  if (const char *e = getenv("CHOL_TRSM_BATCH")) c->trsm_batch = atoi(e);
-  if (const char *e = getenv("CHOL_GEMM_STAGES")) c->gemm_stages = atoi(e);
   if (const char *e = getenv("CHOL_GRAPH")) c->use_graph = atoi(e);
+  for (int r = 0; ngpu > 1 && r < ngpu; r++) {
+    chol_t *s = new chol(c);
+    s->device = devices[r];
+    s->rank = r, s->world = ngpu;
+    s->use_graph = 0;
+    c->sub.push_back(s);
+  }
+  if (ngpu > 1) {
+    c->world = ngpu;
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);  // ranks sharing a device: their streams must not share hardware queues
+  }
   *out = c;
   return 0;
 }
+int chol_num_ranks(chol_t *c) { return is_group(c) ? (int)c->sub.size() : 1; }
+chol_t *chol_rank_handle(chol_t *c, int r) {
+  if (!is_group(c)) return r == 0 ? c : nullptr;
+  return (r >= 0 && r < (int)c->sub.size()) ? c->sub[r] : nullptr;
+}
 
 static void free_solve(chol_t *c);
+static void free_res(chol_t *c);
 static void drop_graph(chol_t *c);
 static void free_device(chol_t *c) {
+  for (chol_t *s : c->sub) free_device(s);
+  c->assembled = c->factored = c->h_fac_valid = false;
   if (!c->device_ready) return;
+  cudaSetDevice(c->device);
   drop_graph(c);
   free_solve(c);
-  cudaSetDevice(c->device);
+  free_res(c);
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
-  cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_info);
+  cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects), cudaFree(c->d_info);
   cudaFree(c->d_diag_off), cudaFree(c->d_diag);
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
-  cudaFree(c->d_flags);
-  c->d_flags = nullptr, c->peers_ready = false;
+  cudaFree(c->d_flags), cudaFree(c->d_counters);
+  c->d_flags = nullptr, c->d_counters = nullptr, c->peers_ready = false;
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   c->h_pinned = nullptr, c->h_pinned_bytes = 0;
   for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
   c->evs.clear();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
-  c->ev_fork = c->ev_join = nullptr;
-  if (c->stream1) cudaStreamDestroy(c->stream1);
-  c->stream1 = nullptr;
-  if (c->stream) cudaStreamDestroy(c->stream);
+  c->ev_fork = nullptr;
+  for (int i = 0; i < kStreams; i++) {
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    c->ev_join[i] = nullptr, c->streams[i] = nullptr;
+  }
   c->device_ready = false;
 }
 
 void chol_destroy(chol_t *c) {
   if (!c) return;
   free_device(c);
+  for (chol_t *s : c->sub) delete s;
   delete c;
 }
 const char *chol_last_error(chol_t *c) { return c ? c->err.c_str() : "null handle"; }
 
-int chol_load(chol_t *c, const char *mtx, const char *ord, const char *clust) {
+// a new problem or partition invalidates everything derived from the old one, on the host and on the device
+static void invalidate(chol_t *c) {
+  free_device(c);
   c->loaded = c->analyzed = false;
+  for (chol_t *s : c->sub) s->loaded = s->analyzed = false;
+}
+
+int chol_load(chol_t *c, const char *mtx, const char *ord, const char *clust) {
+  if (c->parent) return fail(c, "load through the group handle");
+  invalidate(c);
   if (read_problem(c->P, mtx, ord, clust, c->err)) return -1;
   c->loaded = true;
   return 0;
@@ -151,7 +220,8 @@ int chol_load(chol_t *c, const char *mtx, const char *ord, const char *clust) {
 int chol_load_arrays(chol_t *c, int n, int64_t nz, const int32_t *I, const int32_t *J, const double *V, int levels, int nsep,
                      const int64_t *sep_ptr, const int32_t *sep_dofs, const int64_t *sep_iv_ptr, const int64_t *iv_ptr,
                      const int32_t *iv_vals) {
-  c->loaded = c->analyzed = false;
+  if (c->parent) return fail(c, "load through the group handle");
+  invalidate(c);
   Problem &P = c->P;
   P = Problem();
   P.n = P.ncols = n, P.nz = nz;
@@ -178,7 +248,8 @@ int chol_load_arrays(chol_t *c, int n, int64_t nz, const int32_t *I, const int32
 }
 
 int chol_generate(chol_t *c, int nx, int ny, int nz, int stencil, int levels) {
-  c->loaded = c->analyzed = false;
+  if (c->parent) return fail(c, "load through the group handle");
+  invalidate(c);
   if (generate_problem(c->P, nx, ny, nz, stencil, levels, c->err)) return -1;
   c->loaded = true;
   return 0;
@@ -190,14 +261,24 @@ int chol_write_inputs(chol_t *c, const char *mtx, const char *ord, const char *c
 }
 
 int chol_analyze(chol_t *c, int keep_records) {
+  if (c->parent) return fail(c, "analyze through the group handle");
   if (!c->loaded) return fail(c, "load a problem first");
   free_device(c);
   c->analyzed = false;
   if (analyze(c->P, c->S, keep_records != 0, c->err)) return -1;
-  if (build_schedule(c->P, c->S, c->D, c->rank, c->world, false, c->err)) return -1;
+  if (is_group(c)) {  // one symbolic analysis, one schedule per rank
+    std::vector<int> rc(c->sub.size(), 0);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < c->sub.size(); i++)
+      th.emplace_back([&, i] { rc[i] = build_schedule(c->P, c->S, c->sub[i]->D, (int)i, (int)c->sub.size(), false, c->sub[i]->err); });
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < rc.size(); i++) {
+      if (rc[i]) return fail(c, c->sub[i]->err);
+      c->sub[i]->loaded = c->sub[i]->analyzed = true;
+    }
+  } else if (build_schedule(c->P, c->S, c->D, c->rank, c->world, false, c->err))
+    return -1;
   c->analyzed = true;
-  c->assembled = false;
-  c->h_fac_valid = false;
   return 0;
 }
 
@@ -263,21 +344,21 @@ static int upload(chol_t *c, T **dst, const std::vector<T> &src) {
   return 0;
 }
 
-extern "C" {
 static void drop_graph(chol_t *c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   c->graph_exec = nullptr, c->graph_runs = 0;
 }
 static int upload_schedule(chol_t *c) {
   drop_graph(c);  // the captured launches point into the descriptor arrays replaced below
-  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles);
-  c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_potrf = nullptr, c->d_trsm = nullptr, c->d_trsm_tiles = nullptr;
+  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects);
+  c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_potrf = nullptr, c->d_trsm = nullptr, c->d_trsm_tiles = nullptr, c->d_rects = nullptr;
   if (upload(c, &c->d_probs, c->D.probs)) return -100;
   if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
   if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
   if (upload(c, &c->d_potrf, c->D.potrf)) return -100;
   if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
   if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
+  if (upload(c, &c->d_rects, c->D.rects)) return -100;
   return 0;
 }
 // chol_factor runs the fused schedule (pivot block and off-diagonal rows advance together); the
@@ -289,157 +370,161 @@ static int ensure_schedule(chol_t *c, bool split) {
   return upload_schedule(c);
 }
 
-static int ensure_device(chol_t *c) {
+using GemmMain = GemmWsCfg<64, 64, 16, 32, 32, 4>;  // 64x64 CTA tiles, four-stage operand ring, three CTAs per SM
+static int rank_device(chol_t *c) {  // one rank: streams, buffers, descriptor arrays
   if (!c->analyzed) return fail(c, "analyze first");
   if (c->device_ready) return 0;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(c, "no CUDA device: the numeric factorization runs on the GPU only (no CPU fallback)");
+  if (c->device < 0 || c->device >= ndev) return fail(c, "no such CUDA device: " + std::to_string(c->device));
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   {  // the chain stream gets the highest priority: its few CTAs must slip in between the CTAs of a
-     // trailing update that fills the GPU, not queue behind them
+     // trailing update that fills the GPU, not queue behind them; the background pushes get the lowest
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&c->stream1, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&c->streams[0], cudaStreamNonBlocking, std::min(lo, hi + 1)));
+    CK(cudaStreamCreateWithPriority(&c->streams[1], cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&c->streams[2], cudaStreamNonBlocking, lo));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < kStreams; i++) CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
   c->cur = c->stream;
   CK(cudaMalloc((void **)&c->d_fac, (size_t)c->S.total_doubles * sizeof(double)));
   c->device_ready = true;
   if (upload(c, &c->d_vals, c->P.ev)) return -100;
   if (upload(c, &c->d_aoff, c->D.a_off)) return -100;
   if (upload_schedule(c)) return -100;
-  CK(cudaMalloc((void **)&c->d_info, sizeof(int)));
+  CK(cudaMalloc((void **)&c->d_info, 2 * sizeof(int)));
   std::vector<int64_t> doff(c->P.n);
   for (int h = 1; h <= c->P.N; h++)
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
-  CK(cudaFuncSetAttribute(trsm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
-  CK(cudaFuncSetAttribute(trsm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
-  CK(cudaMalloc((void **)&c->d_flags, kMaxPeers * sizeof(unsigned long long)));
-  CK(cudaMemset(c->d_flags, 0, kMaxPeers * sizeof(unsigned long long)));
+  CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMain::kSmemBytes));
+  CK(cudaMalloc((void **)&c->d_flags, kFlagSlots * kMaxPeers * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_flags, 0, kFlagSlots * kMaxPeers * sizeof(unsigned long long)));
+  CK(cudaMalloc((void **)&c->d_counters, kStreams * sizeof(unsigned)));
+  CK(cudaMemset(c->d_counters, 0, kStreams * sizeof(unsigned)));
   c->peers.n = 1, c->peers.rank = 0;
   c->peers.fac[0] = c->d_fac, c->peers.flags[0] = c->d_flags;
   c->peers_ready = (c->world == 1);
-  c->epoch = 0;
+  c->run_id = 0;
+  return 0;
+}
+// a group: every rank's buffers, then peer access between the devices and the peer tables
+static int ensure_device(chol_t *c) {
+  if (!is_group(c)) return rank_device(c);
+  if (!c->analyzed) return fail(c, "analyze first");
+  bool ready = true;
+  for (chol_t *s : c->sub) ready = ready && s->device_ready && s->peers_ready;
+  if (ready) return 0;
+  for (chol_t *s : c->sub)
+    if (rank_device(s)) return fail(c, s->err);
+  const int n = (int)c->sub.size();
+  for (int a = 0; a < n; a++)
+    for (int b = 0; b < n; b++) {
+      const int da = c->sub[a]->device, db = c->sub[b]->device;
+      if (da == db) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, da, db));
+      if (!can) return fail(c, "device " + std::to_string(da) + " cannot map the memory of device " + std::to_string(db));
+      CK(cudaSetDevice(da));
+      cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+      (void)cudaGetLastError();
+    }
+  for (int a = 0; a < n; a++) {
+    chol_t *s = c->sub[a];
+    s->peers.n = n, s->peers.rank = a;
+    for (int b = 0; b < n; b++) s->peers.fac[b] = c->sub[b]->d_fac, s->peers.flags[b] = c->sub[b]->d_flags;
+    s->peers_ready = true;
+  }
+  c->device_ready = true;
   return 0;
 }
 
 static int do_assemble(chol_t *c) {
   CK(cudaMemsetAsync(c->d_fac, 0, (size_t)c->S.total_doubles * sizeof(double), c->stream));
-  int info0 = 0x7fffffff;
-  CK(cudaMemcpyAsync(c->d_info, &info0, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const int info0[2] = {0x7fffffff, 0};
+  CK(cudaMemcpyAsync(c->d_info, info0, sizeof info0, cudaMemcpyHostToDevice, c->stream));
   if (c->P.nz > 0) {
     int64_t nzv = c->P.nz;
     assemble_kernel<<<(unsigned)((nzv + 255) / 256), 256, 0, c->stream>>>(c->d_vals, c->d_aoff, nzv, c->d_fac);
   }
   CK(cudaGetLastError());
   c->assembled = true;
+  c->factored = false;
   c->h_fac_valid = false;
   return 0;
 }
 
-}  // extern "C"
-template <int BM, int BN, int BK, int WM, int WN, int ST>
-static void launch_gemm(chol_t *c, const Launch &l) {
-  using Cfg = GemmCfg<BM, BN, BK, WM, WN, ST>;
-  static bool attr[kMaxDevices][2] = {};  // the opt-in shared-memory size is a per-device function attribute
-  bool &done = attr[c->device % kMaxDevices][(l.shared == 1) ? 1 : 0];
-  if (!done) {
-    if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    else cudaFuncSetAttribute(gemm_grouped<BM, BN, BK, WM, WN, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    done = true;
-  }
-  if (l.shared == 1)
-    gemm_grouped<BM, BN, BK, WM, WN, ST, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
-        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-  else
-    gemm_grouped<BM, BN, BK, WM, WN, ST, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
-        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-}
-template <int BM, int BN, int BK, int WM, int WN, int ST, int MINB>
-static void launch_gemm_ws(chol_t *c, const Launch &l) {
-  using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, ST>;
-  static bool attr[kMaxDevices][2] = {};
-  bool &done = attr[c->device % kMaxDevices][(l.shared == 1) ? 1 : 0];
-  if (!done) {
-    if (l.shared == 1) cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    else cudaFuncSetAttribute(gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    done = true;
-  }
-  if (l.shared == 1)
-    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, true><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
-        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-  else
-    gemm_grouped_ws<BM, BN, BK, WM, WN, ST, MINB, false><<<(unsigned)l.count, Cfg::kThreads, Cfg::kSmemBytes, c->cur>>>(
-        c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac, c->peers);
-}
-extern "C" {
-static void launch_barrier(chol_t *c) {
-  c->epoch++;
-  peer_barrier<<<1, 32, 0, c->cur>>>(c->peers, c->epoch);
-}
-
 static int run_launch(chol_t *c, const Launch &l) {
+  const unsigned long long flag = (c->run_id << 32) | (unsigned long long)l.seq;
   switch (l.kind) {
     case K_POTRF:
-      if (c->potrf_r == 3) potrf_tile_r2<3><<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
-      else if (c->potrf_r == 2) potrf_tile_r2<1><<<(unsigned)l.count, 2 * kNB, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
-      else if (c->potrf_r) potrf_tile_r<<<(unsigned)l.count, kPotrfRThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
-      else if (c->potrf_w) potrf_tile_w<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
-      else potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
+      potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
       break;
     case K_TRSM:
-      if (c->trsm_batch) trsm_tile<true><<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
-      else trsm_tile<false><<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+      trsm_tile<<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
       if (l.count <= 0) break;
       if (l.cfg == 3)
         gemm_small_warp<<<(unsigned)((l.count + kSmallWarps - 1) / kSmallWarps), kSmallWarps * 32, 0, c->cur>>>(
             c->d_probs, c->d_contribs, c->d_tiles + l.begin, l.count, c->d_fac);
-      else if (l.cfg == 2)
-        launch_gemm_ws<128, 64, 16, 32, 32, 4, 2>(c, l);
-      else if (l.cfg == 1)
-        launch_gemm_ws<128, 128, 16, 32, 32, 4, 1>(c, l);
-      else if (c->gemm_ws && c->gemm_stages == 4)  // experimental: four-stage ring (power-of-two indexing), 3 CTAs/SM
-        launch_gemm_ws<64, 64, 16, 32, 32, 4, 3>(c, l);
-      else if (c->gemm_ws)
-        launch_gemm_ws<64, 64, 16, 32, 32, 3, 4>(c, l);
       else
-        launch_gemm<64, 64, 16, 32, 32, 3>(c, l);
+        gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3><<<(unsigned)l.count, GemmMain::kThreads, GemmMain::kSmemBytes, c->cur>>>(
+            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
       break;
-    case K_BARRIER:
-      launch_barrier(c);
+    case K_SYNC:
+      peer_sync<<<1, 32, 0, c->cur>>>(c->peers, l.slot, flag, l.sig_mask, l.wait_mask, c->d_info + 1);
       break;
-    case K_ALLREDUCE:  // one top panel: shared = its heap index, cfg = mask of contributing ranks
-      allreduce_top<<<148 * 4, 256, 0, c->cur>>>(c->peers, l.begin / 2, l.count / 2, c->S.ld[l.shared] / 2, c->P.sz[l.shared],
-                                                 (unsigned)l.cfg);
+    case K_PUSH:
+      if (l.count > 0 && l.mask)
+        push_rects<<<(unsigned)(l.count * (kRowBlock / kPushCols)), kPushThreads, 0, c->cur>>>(c->d_rects + l.begin, c->d_fac, c->peers, l.mask, l.slot,
+                                                                                             flag, l.sig_mask, c->d_counters + l.stream);
+      else if (l.sig_mask)
+        peer_sync<<<1, 32, 0, c->cur>>>(c->peers, l.slot, flag, l.sig_mask, 0u, c->d_info + 1);
       break;
-    case K_NOP:
+    case K_REDUCE: {
+      const int cg = std::max(1, std::min(64, (int)(4 * c->num_sms / std::max<int64_t>(1, l.count))));
+      reduce_rects<<<(unsigned)(l.count * cg), kPushThreads, 0, c->cur>>>(c->d_rects + l.begin, c->d_fac, c->peers, l.mask, cg);
+      break;
+    }
+    default:
       break;
   }
   return 0;
 }
+static bool launches_kernel(const Launch &l) {
+  if (l.kind == K_NOP) return false;
+  if (l.kind == K_GEMM) return l.count > 0;
+  if (l.kind == K_PUSH) return (l.count > 0 && l.mask) || l.sig_mask;
+  return true;
+}
 
+extern "C" {
 static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool per_kernel_timing) {
   if (c->world > 1 && !c->peers_ready) return fail(c, "multi-GPU handle: exchange IPC handles first (chol_ipc_export / chol_ipc_import)");
   std::vector<cudaEvent_t> ev;
   std::vector<int> kinds;
   std::vector<double> fl;
-  // cross-stream events of the launch list (look-ahead); the chain stream starts after whatever is
+  // cross-stream events of the launch list (look-ahead); the other streams start after whatever is
   // already queued on the main stream (assembly)
   while ((int)c->evs.size() < c->D.num_events) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->evs.push_back(e);
   }
-  // graph replay / capture: whole level loop, single GPU, uninstrumented (see chol::use_graph)
   const bool whole = lvl_from >= c->P.levels - 1 && lvl_to <= 0 && phase_mask == 7;
-  const bool graphable = c->use_graph && c->world == 1 && whole && !per_kernel_timing;
+  if (c->world > 1 && !whole) return fail(c, "partial runs of the level loop need a single-GPU handle");
+  if (whole) c->run_id++;
+  // graph replay / capture: whole level loop, single GPU, uninstrumented (see chol::use_graph)
+  const bool want_graph = c->use_graph < 0 ? c->S.flops() < kGraphFlops : c->use_graph != 0;
+  const bool graphable = want_graph && c->world == 1 && whole && !per_kernel_timing;
   if (graphable && c->graph_exec) {
     CK(cudaGraphLaunch(c->graph_exec, c->stream));
     return 0;
@@ -449,13 +534,13 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   if (capture) CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   if (c->D.lookahead) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
-    CK(cudaStreamWaitEvent(c->stream1, c->ev_fork, 0));
+    for (int i = 1; i < kStreams; i++) CK(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
   }
   for (const Launch &l : c->D.launches) {
     if (l.level > lvl_from || l.level < lvl_to) continue;
     if (l.kind != K_NOP && !(l.phase & phase_mask)) continue;
     // the instrumented pass runs everything on one stream so that an event pair brackets one kernel alone
-    c->cur = (l.stream && !per_kernel_timing) ? c->stream1 : c->stream;
+    c->cur = per_kernel_timing ? c->stream : c->streams[l.stream];
     if (l.wait_ev >= 0 && !per_kernel_timing) cudaStreamWaitEvent(c->cur, c->evs[l.wait_ev], 0);
     if (per_kernel_timing) {
       cudaEvent_t a, b;
@@ -469,10 +554,13 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
     if (l.rec_ev >= 0 && !per_kernel_timing) cudaEventRecord(c->evs[l.rec_ev], c->cur);
   }
   c->cur = c->stream;
-  if (c->D.lookahead) {  // partial runs (piecewise calls) may leave work on the chain stream: join it
-    CK(cudaEventRecord(c->ev_join, c->stream1));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if (c->D.lookahead) {  // partial runs (piecewise calls) may leave work on the other streams: join them
+    for (int i = 1; i < kStreams; i++) {
+      CK(cudaEventRecord(c->ev_join[i], c->streams[i]));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+    }
   }
+  if (whole) c->factored = true;
   if (capture) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamEndCapture(c->stream, &g));
@@ -506,32 +594,37 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
 
 int chol_assemble(chol_t *c) {
   if (ensure_device(c)) return -1;
-  if (do_assemble(c)) return -1;
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return for_ranks(c, [](chol_t *r) {
+    chol_t *c = r;
+    if (do_assemble(c)) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  });
 }
 
-// kernels one step launches (the all-reduce is a barrier, the reduction kernel and a barrier)
+// kernels one step launches
 static int64_t count_kernels(chol_t *c) {
   int64_t k = 0;
-  for (const Launch &l : c->D.launches) k += l.kind == K_NOP ? 0 : (l.kind == K_GEMM && l.count <= 0) ? 0 : 1;
+  for (const Launch &l : c->D.launches) k += launches_kernel(l) ? 1 : 0;
   return k;
 }
 
 static int fetch_info(chol_t *c, int *info) {
-  int v = 0;
-  CK(cudaMemcpyAsync(&v, c->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int v[2] = {0, 0};
+  CK(cudaMemcpyAsync(v, c->d_info, sizeof v, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  *info = (v == 0x7fffffff) ? 0 : v;
+  *info = (v[0] == 0x7fffffff) ? 0 : v[0];
+  if (v[1]) return fail(c, "a wait on a peer GPU timed out (a rank of the partition is missing or failed)");
   return 0;
 }
+static int info_error(chol_t *c, int info) {
+  c->factored = false;  // the panels past the bad pivot are meaningless: results and solves are refused
+  return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+}
 
-int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
-  if (ensure_device(c)) return -1;
+// one rank: `warmup + iterations` x (assemble; level loop), device time of every timed level loop
+static int factor_rank(chol_t *c, int iterations, int warmup, std::vector<double> &secs, double &asm_s, int &info) {
   if (ensure_schedule(c, false)) return -1;
-  if (iterations < 1) iterations = 1;
-  std::vector<double> secs;
-  double asm_s = 0;
   cudaEvent_t e0, e1, e2;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -549,41 +642,68 @@ int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
     if (it >= warmup) secs.push_back(mf * 1e-3), asm_s = ma * 1e-3;
   }
   cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2);
-  int info = 0;
-  if (fetch_info(c, &info)) return -1;
+  return fetch_info(c, &info);
+}
+
+int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
+  if (c->parent) return fail(c, "factor through the group handle");
+  if (ensure_device(c)) return -1;
+  if (iterations < 1) iterations = 1;
+  const int nr = chol_num_ranks(c);
+  std::vector<std::vector<double>> secs(nr);
+  std::vector<double> asm_s(nr, 0.0);
+  std::vector<int> info(nr, 0);
+  if (for_ranks(c, [&](chol_t *r) { return factor_rank(r, iterations, warmup, secs[r->parent ? r->rank : 0], asm_s[r->parent ? r->rank : 0], info[r->parent ? r->rank : 0]); }))
+    return -1;
+  // a step of a group takes as long as its slowest rank
+  std::vector<double> step(iterations, 0.0);
+  double as = 0;
+  int bad = 0;
+  for (int r = 0; r < nr; r++) {
+    for (int i = 0; i < iterations; i++) step[i] = std::max(step[i], secs[r][i]);
+    as = std::max(as, asm_s[r]);
+    if (info[r] && (!bad || info[r] < bad)) bad = info[r];
+  }
   if (st) {
-    std::vector<double> s = secs;
+    std::vector<double> s = step;
     std::sort(s.begin(), s.end());
     st->seconds_best = s.front();
     st->seconds_median = s[s.size() / 2];
-    st->seconds_last = secs.back();
-    st->assemble_seconds = asm_s;
+    st->seconds_last = step.back();
+    st->assemble_seconds = as;
     st->flops = c->S.flops();
-    st->kernel_launches = count_kernels(c);
-    st->info = info;
+    st->kernel_launches = 0;
+    for (int r = 0; r < nr; r++) st->kernel_launches += count_kernels(chol_rank_handle(c, r));
+    st->info = bad;
   }
-  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  c->assembled = c->factored = true;
+  if (bad) {
+    for (int r = 0; r < nr; r++) chol_rank_handle(c, r)->factored = false;
+    return info_error(c, bad);
+  }
   return 0;
 }
 
 static int piecewise(chol_t *c, int lvl, int phase) {
+  if (is_group(c) || c->world > 1) return fail(c, "the piecewise fused tasks run on a single-GPU handle");
   if (ensure_device(c)) return -1;
+  cudaSetDevice(c->device);
   if (!c->assembled) return fail(c, "assemble first");
   if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
   if (ensure_schedule(c, phase != PH_UPDATE || c->D.split_phases)) return -1;
   c->h_fac_valid = false;
   if (run_levels(c, lvl, lvl, phase, false)) return -1;
   CK(cudaStreamSynchronize(c->stream));
+  if (lvl == 0 && phase == PH_POTRF) c->factored = true;  // the last fused task of the level loop (the root has no ancestors)
   return 0;
 }
 int chol_fused_dpotrf(chol_t *c, int lvl) { return piecewise(c, lvl, PH_POTRF); }
 int chol_fused_dtrsm(chol_t *c, int lvl) { return piecewise(c, lvl, PH_TRSM); }
 int chol_fused_update(chol_t *c, int lvl) { return piecewise(c, lvl, PH_UPDATE); }
 
-int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_out, chol_stats_t *st) {
-  if (ensure_device(c)) return -1;
+// one rank of chol_factor_host: H2D of the values, assemble, level loop, D2H of diag(L)
+static int factor_host_rank(chol_t *c, const double *values, double &secs, int &info) {
   if (ensure_schedule(c, false)) return -1;
-  if (values && nz != c->P.nz) return fail(c, "value count differs from the loaded pattern");
   size_t need = std::max((size_t)c->P.nz, (size_t)c->P.n) * sizeof(double);
   if (c->h_pinned_bytes < need) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -606,28 +726,65 @@ int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_o
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0), cudaEventDestroy(e1);
-  if (diag_out) memcpy(diag_out, c->h_pinned, (size_t)c->P.n * sizeof(double));
-  int info = 0;
-  if (fetch_info(c, &info)) return -1;
+  secs = ms * 1e-3;
+  return fetch_info(c, &info);
+}
+// does this rank report separator h (its own subtree; rank 0 also the top panels, which every rank holds complete)
+static bool reports(const chol_t *c, int h) {
+  if (c->world == 1) return true;
+  const int lv = c->P.level_of(h), own = lv < c->D.depth ? -1 : (h >> (lv - c->D.depth)) - (1 << c->D.depth);
+  return own == c->rank || (own < 0 && c->rank == 0);
+}
+
+int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_out, chol_stats_t *st) {
+  if (c->parent) return fail(c, "factor through the group handle");
+  if (ensure_device(c)) return -1;
+  if (values && nz != c->P.nz) return fail(c, "value count differs from the loaded pattern");
+  const int nr = chol_num_ranks(c);
+  std::vector<double> secs(nr, 0.0);
+  std::vector<int> info(nr, 0);
+  if (for_ranks(c, [&](chol_t *r) { return factor_host_rank(r, values, secs[r->parent ? r->rank : 0], info[r->parent ? r->rank : 0]); })) return -1;
+  double worst = 0;
+  int bad = 0;
+  int64_t kernels = 0;
+  for (int r = 0; r < nr; r++) {
+    chol_t *rk = chol_rank_handle(c, r);
+    worst = std::max(worst, secs[r]);
+    if (info[r] && (!bad || info[r] < bad)) bad = info[r];
+    kernels += count_kernels(rk) + 2;
+    if (diag_out)  // every rank hands back the diagonal entries of the separators it reports (zeros elsewhere on a partitioned handle)
+      for (int h = 1; h <= c->P.N; h++) {
+        const bool mine = reports(rk, h);
+        if (!mine && is_group(c)) continue;
+        for (int i = 0; i < c->P.sz[h]; i++) diag_out[c->P.start[h] + i] = mine ? rk->h_pinned[c->P.start[h] + i] : 0.0;
+      }
+  }
   if (st) {
-    st->seconds_best = st->seconds_median = st->seconds_last = ms * 1e-3;
+    st->seconds_best = st->seconds_median = st->seconds_last = worst;
     st->assemble_seconds = 0;
     st->flops = c->S.flops();
-    st->kernel_launches = count_kernels(c) + 2;
-    st->info = info;
+    st->kernel_launches = kernels;
+    st->info = bad;
   }
-  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  c->assembled = c->factored = true;
+  if (bad) {
+    for (int r = 0; r < nr; r++) chol_rank_handle(c, r)->factored = false;
+    return info_error(c, bad);
+  }
   return 0;
 }
 
-/* ---- multi-GPU plumbing */
+/* ---- multi-GPU plumbing, one process per GPU */
 int chol_set_partition(chol_t *c, int rank, int world) {
+  if (is_group(c) || c->parent) return fail(c, "a group handle is partitioned by chol_create");
   if (world < 1 || world > kMaxPeers || (world & (world - 1)) || rank < 0 || rank >= world) return fail(c, "world must be 1, 2, 4 or 8 and 0 <= rank < world");
+  free_device(c);
   c->rank = rank, c->world = world;
   c->analyzed = false;
   return 0;
 }
 int chol_ipc_export(chol_t *c, void *handles128) {
+  if (is_group(c) || c->parent) return fail(c, "the ranks of a group handle share one process: nothing to export");
   if (ensure_device(c)) return -1;
   cudaIpcMemHandle_t h[2];
   CK(cudaIpcGetMemHandle(&h[0], c->d_fac));
@@ -637,6 +794,7 @@ int chol_ipc_export(chol_t *c, void *handles128) {
   return 0;
 }
 int chol_ipc_import(chol_t *c, const void *all_handles, int world) {
+  if (is_group(c) || c->parent) return fail(c, "the ranks of a group handle share one process: nothing to import");
   if (ensure_device(c)) return -1;
   if (world != c->world) return fail(c, "world size mismatch");
   const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
@@ -655,14 +813,18 @@ int chol_ipc_import(chol_t *c, const void *all_handles, int world) {
   c->peers_ready = true;
   return 0;
 }
+static chol_t *first_rank(chol_t *c) { return is_group(c) ? c->sub[0] : c; }
 /* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
- * [2] shared (tile-split) launches, [3] doubles of the shared top region, [4] potrf tiles, [5] trsm slabs */
+ * [2] peer-store launches (rows pushed to other ranks), [3] doubles of the top panels (one copy per rank),
+ * [4] potrf tiles, [5] trsm slabs.  On a group handle: rank 0 (chol_rank_handle gives the others). */
 int chol_partition_stats(chol_t *c, double *out6) {
   if (!c->analyzed) return fail(c, "analyze first");
+  c = first_rank(c);
   double a = 0, f = 0, sh = 0, pt = 0, ts = 0;
   for (int64_t o : c->D.a_off) a += (o >= 0);
   for (const Launch &l : c->D.launches) {
-    if (l.kind == K_GEMM) f += l.flops, sh += (l.shared == 1);
+    if (l.kind == K_GEMM) f += l.flops;
+    if (l.kind == K_PUSH) sh += (l.count > 0 && l.mask);
     if (l.kind == K_POTRF) pt += (double)l.count;
     if (l.kind == K_TRSM) ts += (double)l.count;
   }
@@ -677,6 +839,7 @@ int chol_partition_stats(chol_t *c, double *out6) {
 int chol_level_bytes(chol_t *c, int lvl, double *out3) {
   if (!c->analyzed) return fail(c, "analyze first");
   if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
+  if (is_group(c) || c->world > 1) return fail(c, "chol_level_bytes: single-GPU handles");
   const Problem &P = c->P;
   const Symbolic &S = c->S;
   double panel = 0, oper = 0, dest = 0;
@@ -695,10 +858,41 @@ int chol_level_bytes(chol_t *c, int lvl, double *out3) {
       if (p == last) continue;  // the tiles of one problem are consecutive
       last = p;
       const GemmProblem &g = c->D.probs[p];
-      dest += 16.0 * ((double)g.M * g.N - (g.tri ? 0.5 * g.N * (g.N - 1.0) : 0.0));
+      dest += 16.0 * ((double)g.M * g.N - ((g.tri & 1) ? 0.5 * g.N * (g.N - 1.0) : 0.0));
     }
   }
   out3[0] = panel, out3[1] = oper, out3[2] = dest;
+  return 0;
+}
+/* Largest |difference| between this rank's copy of the factored top panels (lower triangle of the pivot blocks and
+ * every stored off-diagonal row) and the copy of the next rank, compared on the GPU through peer memory; on a group
+ * handle the largest over all ranks (so 0 means all copies are bit-identical).  0 on a single-GPU handle. */
+static int top_diff_rank(chol_t *c, double *out) {
+  *out = 0;
+  if (c->world == 1) return 0;
+  if (!c->device_ready || !c->factored || !c->peers_ready) return fail(c, "factor first");
+  std::vector<RectDesc> rects;
+  for (int h = 1; h < (1 << c->D.depth); h++)
+    if (c->P.sz[h] > 0) rects.push_back(RectDesc{c->S.poff[h], c->S.ld[h], c->S.rows[h], c->P.sz[h], 0});
+  if (rects.empty()) return 0;
+  RectDesc *d_r = nullptr;
+  unsigned long long *d_w = nullptr, w = 0;
+  if (upload(c, &d_r, rects)) return -100;
+  CK(cudaMalloc((void **)&d_w, sizeof w));
+  CK(cudaMemsetAsync(d_w, 0, sizeof w, c->stream));
+  const int cg = std::max(1, 4 * c->num_sms / (int)rects.size());
+  compare_rects<<<(unsigned)(rects.size() * cg), kPushThreads, 0, c->stream>>>(d_r, c->d_fac, c->peers, (c->rank + 1) % c->world, cg, d_w);
+  CK(cudaMemcpyAsync(&w, d_w, sizeof w, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_r), cudaFree(d_w);
+  memcpy(out, &w, sizeof w);
+  return 0;
+}
+int chol_top_copies_diff(chol_t *c, double *maxdiff) {
+  const int nr = chol_num_ranks(c);
+  std::vector<double> d(nr, 0.0);
+  if (for_ranks(c, [&](chol_t *r) { return top_diff_rank(r, &d[r->parent ? r->rank : 0]); })) return -1;
+  *maxdiff = *std::max_element(d.begin(), d.end());
   return 0;
 }
 int chol_rank(chol_t *c) { return c->rank; }
@@ -706,33 +900,45 @@ int chol_world(chol_t *c) { return c->world; }
 
 /* per-launch device time (ms) of the last chol_kernel_times pass, in launch-list order */
 int64_t chol_launch_times(chol_t *c, float *ms, int64_t cap) {
+  c = first_rank(c);
   int64_t n = std::min<int64_t>(cap, (int64_t)c->launch_ms.size());
   for (int64_t i = 0; i < n; i++) ms[i] = c->launch_ms[i];
   return (int64_t)c->launch_ms.size();
 }
-int64_t chol_num_launches(chol_t *c) { return c->analyzed ? (int64_t)c->D.launches.size() : -1; }
+int64_t chol_num_launches(chol_t *c) { return c->analyzed ? (int64_t)first_rank(c)->D.launches.size() : -1; }
 int chol_get_launch(chol_t *c, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg) {
-  if (!c->analyzed || i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
+  if (!c->analyzed) return -1;
+  c = first_rank(c);
+  if (i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
   const Launch &l = c->D.launches[i];
-  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg | (l.shared << 4);
+  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg | (l.stream << 4);
   return 0;
 }
 
 int chol_synchronize(chol_t *c) {
   if (!c->device_ready) return 0;
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return for_ranks(c, [](chol_t *r) {
+    chol_t *c = r;
+    for (int i = 0; i < kStreams; i++) CK(cudaStreamSynchronize(c->streams[i]));
+    return 0;
+  });
 }
 
+/* one instrumented factorization: everything on one stream per rank, CUDA events around every launch */
 int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops) {
+  if (c->parent) return fail(c, "through the group handle");
   if (ensure_device(c)) return -1;
-  if (ensure_schedule(c, false)) return -1;
-  if (do_assemble(c)) return -1;
-  if (run_levels(c, c->P.levels - 1, 0, 7, true)) return -1;
-  if (potrf_ms) *potrf_ms = c->k_ms[K_POTRF];
-  if (trsm_ms) *trsm_ms = c->k_ms[K_TRSM];
-  if (gemm_ms) *gemm_ms = c->k_ms[K_GEMM];
-  if (gemm_flops) *gemm_flops = c->k_gemm_flops;
+  if (for_ranks(c, [](chol_t *r) {
+        if (ensure_schedule(r, false)) return -1;
+        if (do_assemble(r)) return -1;
+        return run_levels(r, r->P.levels - 1, 0, 7, true);
+      }))
+    return -1;
+  chol_t *r = first_rank(c);
+  if (potrf_ms) *potrf_ms = r->k_ms[K_POTRF];
+  if (trsm_ms) *trsm_ms = r->k_ms[K_TRSM];
+  if (gemm_ms) *gemm_ms = r->k_ms[K_GEMM];
+  if (gemm_flops) *gemm_flops = r->k_gemm_flops;
   return 0;
 }
 
@@ -741,8 +947,30 @@ static int fetch_factor(chol_t *c) {
   if (!c->device_ready || !c->assembled) return fail(c, "nothing factored yet");
   if (c->h_fac_valid) return 0;
   c->h_fac.resize((size_t)c->S.total_doubles);
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(c->h_fac.data(), c->d_fac, (size_t)c->S.total_doubles * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!is_group(c)) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->h_fac.data(), c->d_fac, (size_t)c->S.total_doubles * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    // a group: the top panels from rank 0 (every rank holds them complete), every subtree from its owner; the
+    // panels of one rank on one tree level are contiguous in the factor buffer
+    const Problem &P = c->P;
+    const Symbolic &S = c->S;
+    const int world = (int)c->sub.size(), depth = c->sub[0]->D.depth;
+    auto copy = [&](chol_t *r, int h0, int h1) -> int {
+      const int64_t o0 = S.poff[h0], o1 = S.poff[h1];
+      CK(cudaSetDevice(r->device));
+      CK(cudaStreamSynchronize(r->stream));
+      if (o1 > o0) CK(cudaMemcpy(c->h_fac.data() + o0, r->d_fac + o0, (size_t)(o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost));
+      return 0;
+    };
+    if (copy(c->sub[0], 1, 1 << depth)) return -100;
+    for (int lvl = depth; lvl < P.levels; lvl++)
+      for (int r = 0; r < world; r++) {
+        const int h0 = ((1 << depth) + r) << (lvl - depth);
+        if (copy(c->sub[r], h0, h0 + (1 << (lvl - depth)))) return -100;
+      }
+  }
   c->h_fac_valid = true;
   return 0;
 }
@@ -762,10 +990,7 @@ static void visit(chol_t *c, F fn) {
       for (int hc = hr << d; hc < ((hr + 1) << d); hc++) cols.push_back(hc);
     std::sort(cols.begin(), cols.end(), [](int a, int b) { return a > b; });  // ascending label
     for (int hc : cols) {
-      if (c->world > 1) {  // a rank reports its own subtree; rank 0 also the shared top panels
-        int lvc = P.level_of(hc), own = lvc < c->D.depth ? -1 : (hc >> (lvc - c->D.depth)) - (1 << c->D.depth);
-        if (!(own == c->rank || (own < 0 && c->rank == 0))) continue;
-      }
+      if (!is_group(c) && !reports(c, hc)) continue;  // a rank reports its own subtree; rank 0 also the top panels
       const double *pan = c->h_fac.data() + S.poff[hc];
       int ld = S.ld[hc];
       for (int64_t s = S.seg_ptr[hc]; s < S.seg_ptr[hc + 1]; s++) {
@@ -823,6 +1048,7 @@ int chol_write_factor(chol_t *c, const char *path, int full) {
 
 int chol_write_factor_binary(chol_t *c, const char *path) {
   if (fetch_factor(c)) return -1;
+  if (is_group(c)) return write_factor_binary(c->P, c->S, c->h_fac.data(), 0, 1, 0, path, c->err) ? -1 : 0;
   return write_factor_binary(c->P, c->S, c->h_fac.data(), c->rank, c->world, c->D.depth, path, c->err) ? -1 : 0;
 }
 
@@ -887,6 +1113,7 @@ int chol_factor_debug(chol_t *c, const char *dir, int full_precision, int with_t
   if (c->world > 1) return fail(c, "the debug trace runs on a single-GPU handle");
   if (c->P.n > 20000) return fail(c, "the debug trace writes the whole factor after every fused task: small problems only (n <= 20000)");
   if (ensure_device(c)) return -1;
+  CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   if (do_assemble(c)) return -1;
   Schedule saved = std::move(c->D);
@@ -914,60 +1141,127 @@ int chol_factor_debug(chol_t *c, const char *dir, int full_precision, int with_t
   if (rc) return rc;
   int info = 0;
   if (fetch_info(c, &info)) return -1;
-  if (info != 0) return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
+  if (info != 0) return info_error(c, info);
+  c->factored = true;
   return 0;
 }
 
-int chol_residual(chol_t *c, int k, uint64_t seed, double *rel) {
-  // host evaluation over the stored pattern: R = A W - L (L^T W)
-  if (fetch_factor(c)) return -1;
+}  // extern "C"
+// ------------------------------------------------------------------------------ residual check on the GPU
+struct ResDev {
+  ResPanel *panels = nullptr;
+  ResTile *t_ltw = nullptr, *t_ly = nullptr;
+  int *rowmap = nullptr;
+  double *y = nullptr, *z = nullptr;
+  int64_t n_ltw = 0, n_ly = 0;
+};
+static void free_res(chol_t *c) {
+  ResDev *v = c->res;
+  if (!v) return;
+  cudaFree(v->panels), cudaFree(v->t_ltw), cudaFree(v->t_ly), cudaFree(v->rowmap), cudaFree(v->y), cudaFree(v->z);
+  delete v;
+  c->res = nullptr;
+}
+static int ensure_res(chol_t *c) {
+  if (c->res) return 0;
   const Problem &P = c->P;
   const Symbolic &S = c->S;
-  size_t n = (size_t)P.n;
-  if (k < 1) k = 1;
-  std::vector<double> W(n * k), Y(n * k, 0.0), Z(n * k, 0.0), AW(n * k, 0.0);
-  uint64_t s = seed ? seed : 1;
-  for (auto &w : W) {
-    s = mix64(s);
-    w = (s & 1) ? 1.0 : -1.0;
+  std::vector<ResPanel> panels;
+  std::vector<ResTile> ltw, ly;
+  std::vector<int> rowmap;
+  for (int h = 1; h <= P.N; h++) {
+    if (!reports(c, h) || P.sz[h] == 0) continue;
+    const int n = P.sz[h], r0 = (n + 1) / 2 * 2, rows = S.rows[h];
+    ResPanel rp{S.poff[h], (int64_t)rowmap.size(), S.ld[h], n, rows, r0, P.start[h], 0};
+    rowmap.resize(rowmap.size() + (size_t)std::max(0, rows - r0), -1);
+    for (int64_t s = S.seg_ptr[h] + 1; s < S.seg_ptr[h + 1]; s++) {
+      const Seg &sg = S.segs[s];
+      for (int r = 0; r < sg.hi - sg.lo; r++) rowmap[rp.map_off + (sg.off - r0) + r] = P.start[sg.anc] + sg.lo + r;
+    }
+    const int pi = (int)panels.size();
+    panels.push_back(rp);
+    for (int c0 = 0; c0 < n; c0 += kResColG) ltw.push_back(ResTile{pi, c0, 0, 0});
+    for (int sl = 0; sl * kResSlab < rows; sl++)
+      for (int ch = 0; ch * kResChunk < n; ch++) {
+        const int rlast = std::min(rows, (sl + 1) * kResSlab) - 1;
+        if (rlast < n && rlast < ch * kResChunk) continue;  // wholly above the diagonal of the pivot block
+        ly.push_back(ResTile{pi, sl, ch, 0});
+      }
   }
-  // W is indexed by permuted row
+  ResDev *v = c->res = new ResDev();
+  v->n_ltw = (int64_t)ltw.size(), v->n_ly = (int64_t)ly.size();
+  if (upload(c, &v->panels, panels) || upload(c, &v->t_ltw, ltw) || upload(c, &v->t_ly, ly) || upload(c, &v->rowmap, rowmap)) return -100;
+  CK(cudaMalloc((void **)&v->y, std::max<size_t>(1, (size_t)P.n * kResK) * sizeof(double)));
+  CK(cudaMalloc((void **)&v->z, std::max<size_t>(1, (size_t)P.n * kResK) * sizeof(double)));
+  return 0;
+}
+// this rank's part of Z = L (L^T W): the panels it reports, read where they sit; z_out is n x kResK, permuted rows
+static int residual_rank(chol_t *c, int k, uint64_t seed, double *z_out) {
+  if (!c->device_ready || !c->factored) return fail(c, "factor first");
+  if (ensure_res(c)) return -1;
+  ResDev *v = c->res;
+  const size_t bytes = (size_t)c->P.n * kResK * sizeof(double);
+  CK(cudaMemsetAsync(v->y, 0, bytes, c->stream));
+  CK(cudaMemsetAsync(v->z, 0, bytes, c->stream));
+  if (v->n_ltw) res_ltw<<<(unsigned)v->n_ltw, kResColG * 32, 0, c->stream>>>(v->panels, v->t_ltw, v->rowmap, c->d_fac, k, seed, v->y);
+  if (v->n_ly) res_ly<<<(unsigned)v->n_ly, kResSlab, 0, c->stream>>>(v->panels, v->t_ly, v->rowmap, c->d_fac, k, v->y, v->z);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(z_out, v->z, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" {
+/* Z_partial = L_r (L_r^T W) over the panels this handle reports, W = k <= 4 Rademacher columns generated from
+ * `seed`; z_out holds n x 4 doubles (row = permuted row, first k columns used).  The sum over the ranks of a
+ * partition goes to chol_residual_finish. */
+int chol_residual_partial(chol_t *c, int k, uint64_t seed, double *z_out) {
+  if (k < 1 || k > kResK) return fail(c, "1 <= k <= 4 probe columns");
+  if (!is_group(c)) {
+    cudaSetDevice(c->device);
+    return residual_rank(c, k, seed, z_out);
+  }
+  const size_t len = (size_t)c->P.n * kResK;
+  std::vector<std::vector<double>> part(c->sub.size(), std::vector<double>(len));
+  if (for_ranks(c, [&](chol_t *r) { return residual_rank(r, k, seed, part[r->rank].data()); })) return -1;
+  for (size_t i = 0; i < len; i++) {
+    double s = 0;
+    for (auto &pz : part) s += pz[i];
+    z_out[i] = s;
+  }
+  return 0;
+}
+/* rel = ||A W - Z||_F / ||A W||_F with the same W (host: A W from the loaded entries, O(nz k)) */
+int chol_residual_finish(chol_t *c, int k, uint64_t seed, const double *z_sum, double *rel) {
+  if (k < 1 || k > kResK) return fail(c, "1 <= k <= 4 probe columns");
+  const Problem &P = c->P;
+  const size_t n = (size_t)P.n;
+  std::vector<double> AW(n * kResK, 0.0);
   std::vector<int> iperm(n);
   for (int p = 0; p < P.n; p++) iperm[P.perm[p]] = p;
   for (int64_t e = 0; e < P.nz; e++) {
-    int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
-    double v = P.ev[e];
+    const int pi = iperm[P.ei[e]], pj = iperm[P.ej[e]];
+    const double v = P.ev[e];
     for (int q = 0; q < k; q++) {
-      AW[(size_t)pi * k + q] += v * W[(size_t)pj * k + q];
-      if (pi != pj) AW[(size_t)pj * k + q] += v * W[(size_t)pi * k + q];
+      AW[(size_t)pi * kResK + q] += v * res_w(seed, pj, q);
+      if (pi != pj) AW[(size_t)pj * kResK + q] += v * res_w(seed, pi, q);
     }
   }
-  // Y = L^T W (by columns of L), Z = L Y
-  for (int pass = 0; pass < 2; pass++)
-    for (int hc = 1; hc <= P.N; hc++) {
-      const double *pan = c->h_fac.data() + S.poff[hc];
-      int ld = S.ld[hc];
-      for (int64_t sgi = S.seg_ptr[hc]; sgi < S.seg_ptr[hc + 1]; sgi++) {
-        const Seg &sg = S.segs[sgi];
-        bool diag = sg.anc == hc;
-        for (int col = 0; col < P.sz[hc]; col++) {
-          size_t gc = (size_t)P.start[hc] + col;
-          for (int r = diag ? col : 0; r < sg.hi - sg.lo; r++) {
-            double v = pan[sg.off + r + (size_t)col * ld];
-            if (v == 0) continue;
-            size_t gr = (size_t)P.start[sg.anc] + sg.lo + r;
-            for (int q = 0; q < k; q++) {
-              if (pass == 0) Y[gc * k + q] += v * W[gr * k + q];
-              else Z[gr * k + q] += v * Y[gc * k + q];
-            }
-          }
-        }
-      }
-    }
   double num = 0, den = 0;
-  for (size_t i = 0; i < n * k; i++) num += (AW[i] - Z[i]) * (AW[i] - Z[i]), den += AW[i] * AW[i];
+  for (size_t i = 0; i < n; i++)
+    for (int q = 0; q < k; q++) {
+      const double a = AW[i * kResK + q], d = a - z_sum[i * kResK + q];
+      num += d * d, den += a * a;
+    }
   *rel = std::sqrt(num / (den > 0 ? den : 1));
   return 0;
+}
+/* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F on a single-GPU or group handle */
+int chol_residual(chol_t *c, int k, uint64_t seed, double *rel) {
+  if (!is_group(c) && c->world > 1) return fail(c, "partitioned handle: sum chol_residual_partial over the ranks, then chol_residual_finish");
+  k = std::max(1, std::min(k, kResK));
+  std::vector<double> z((size_t)c->P.n * kResK);
+  if (chol_residual_partial(c, k, seed ? seed : 1, z.data())) return -1;
+  return chol_residual_finish(c, k, seed ? seed : 1, z.data(), rel);
 }
 
 // ------------------------------------------------------------------------------ solve on the GPU
@@ -1047,36 +1341,11 @@ static size_t solve_exchange_index(const SolveSchedule &V) {
   return V.launches.size();
 }
 
-/* mmat.rg:1364-1495: permute b, forward substitution leaves -> root, backward root -> leaves, un-permute. */
-int chol_solve(chol_t *c, const double *b, double *x) {
-  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
-  if (c->world > 1)
-    return fail(c, "chol_solve runs on a single-GPU handle; on a partitioned handle use chol_solve_forward / chol_solve_backward "
-                   "with a sum of the top part over the ranks in between");
-  if (ensure_solve(c)) return -1;
-  SolveDev *v = c->solve;
-  const int n = c->P.n;
-  cudaStream_t st = c->stream;
-  CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-  permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
-  run_solve_launches(c, 0, v->V.launches.size());
-  permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->x, v->perm, n, v->io);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(x, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return 0;
-}
-
-/* The same sweeps on a partitioned handle (one process per GPU, section 6 of DESIGN.md).  Forward: the rank's
- * subtree; its pulls leave in the top rows only this rank's contributions (rank 0 starts them from b, the
- * others from zero), so the SUM of top_partial over the ranks is the right-hand side the top levels see. */
-int64_t chol_solve_top_size(chol_t *c) {
-  if (!c->analyzed) return -1;
-  if (c->world == 1) return 0;
-  return (int64_t)c->P.n - c->P.start[(1 << c->D.depth) - 1];
-}
-int chol_solve_forward(chol_t *c, const double *b, double *top_partial) {
-  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+// one rank, forward: the rank's subtree; its pulls leave in the top rows only this rank's contributions (rank 0
+// starts them from b, the others from zero), so the SUM of top_partial over the ranks is the right-hand side
+// the top levels see
+static int solve_forward_rank(chol_t *c, const double *b, double *top_partial) {
+  if (!c->device_ready || !c->factored) return fail(c, "factor first");
   if (ensure_solve(c)) return -1;
   SolveDev *v = c->solve;
   const int n = c->P.n, t0 = v->V.top_row0;
@@ -1090,10 +1359,10 @@ int chol_solve_forward(chol_t *c, const double *b, double *top_partial) {
   CK(cudaStreamSynchronize(st));
   return 0;
 }
-/* top_sum: the sum of every rank's top_partial.  x_owned (original dof order): the entries of the rank's own
- * separators (rank 0: also of the shared top), zeros elsewhere, so that the sum over the ranks is the solution. */
-int chol_solve_backward(chol_t *c, const double *top_sum, double *x_owned) {
-  if (!c->device_ready || !c->assembled) return fail(c, "factor first");
+// top_sum: the sum of every rank's top_partial.  x_owned (original dof order): the entries of the separators
+// the rank reports, zeros elsewhere, so that the sum over the ranks is the solution.
+static int solve_backward_rank(chol_t *c, const double *top_sum, double *x_owned) {
+  if (!c->device_ready || !c->factored) return fail(c, "factor first");
   if (!c->solve || !c->solve->ready) return fail(c, "chol_solve_forward first");
   SolveDev *v = c->solve;
   const Problem &P = c->P;
@@ -1107,16 +1376,74 @@ int chol_solve_backward(chol_t *c, const double *top_sum, double *x_owned) {
   CK(cudaStreamSynchronize(st));
   if (c->world > 1)
     for (int h = 1; h <= P.N; h++) {
-      const int lv = P.level_of(h), own = lv < c->D.depth ? -1 : (h >> (lv - c->D.depth)) - (1 << c->D.depth);
-      if (own == c->rank || (own < 0 && c->rank == 0)) continue;
+      if (reports(c, h)) continue;
       for (int i = 0; i < P.sz[h]; i++) x_owned[P.perm[P.start[h] + i]] = 0.0;
     }
   return 0;
+}
+
+/* mmat.rg:1364-1495: permute b, forward substitution leaves -> root, backward root -> leaves, un-permute.
+ * On a group handle every rank sweeps its subtree, the top rows of the right-hand side are summed over the
+ * ranks on the host (chol_solve_top_size doubles per rank), every rank sweeps the top levels and its subtree
+ * backwards and the owned pieces of x are merged. */
+int chol_solve(chol_t *c, const double *b, double *x) {
+  if (!is_group(c)) {
+    if (c->world > 1)
+      return fail(c, "chol_solve runs on a single-GPU or group handle; on a partitioned handle use chol_solve_forward / "
+                     "chol_solve_backward with a sum of the top part over the ranks in between");
+    if (!c->device_ready || !c->factored) return fail(c, "factor first");
+    cudaSetDevice(c->device);
+    if (ensure_solve(c)) return -1;
+    SolveDev *v = c->solve;
+    const int n = c->P.n;
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(v->io, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    permute_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->io, v->perm, n, v->x);
+    run_solve_launches(c, 0, v->V.launches.size());
+    permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(v->x, v->perm, n, v->io);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x, v->io, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (!c->factored) return fail(c, "factor first");
+  const int nr = (int)c->sub.size(), n = c->P.n;
+  const int64_t nt = chol_solve_top_size(c->sub[0]);
+  std::vector<std::vector<double>> top(nr, std::vector<double>((size_t)std::max<int64_t>(nt, 1))), xs(nr, std::vector<double>((size_t)n));
+  if (for_ranks(c, [&](chol_t *r) { return solve_forward_rank(r, b, top[r->rank].data()); })) return -1;
+  for (int r = 1; r < nr; r++)
+    for (int64_t i = 0; i < nt; i++) top[0][i] += top[r][i];
+  if (for_ranks(c, [&](chol_t *r) { return solve_backward_rank(r, top[0].data(), xs[r->rank].data()); })) return -1;
+  for (int i = 0; i < n; i++) {
+    double v = 0;
+    for (int r = 0; r < nr; r++) v += xs[r][i];
+    x[i] = v;
+  }
+  return 0;
+}
+
+/* The same sweeps on a partitioned handle (one process per GPU, section 6 of DESIGN.md). */
+int64_t chol_solve_top_size(chol_t *c) {
+  if (!c->analyzed) return -1;
+  c = first_rank(c);
+  if (c->world == 1) return 0;
+  return (int64_t)c->P.n - c->P.start[(1 << c->D.depth) - 1];
+}
+int chol_solve_forward(chol_t *c, const double *b, double *top_partial) {
+  if (is_group(c)) return fail(c, "chol_solve does this on a group handle");
+  cudaSetDevice(c->device);
+  return solve_forward_rank(c, b, top_partial);
+}
+int chol_solve_backward(chol_t *c, const double *top_sum, double *x_owned) {
+  if (is_group(c)) return fail(c, "chol_solve does this on a group handle");
+  cudaSetDevice(c->device);
+  return solve_backward_rank(c, top_sum, x_owned);
 }
 /* what the rank's solve schedule covers, [0..5] on its subtree levels and [6..11] on the shared top levels:
  * forward tiles, forward gemv slabs, pull slabs, gather column groups, backward tiles, backward gemv groups */
 int chol_solve_stats(chol_t *c, double *out12) {
   if (!c->analyzed) return fail(c, "analyze first");
+  c = first_rank(c);
   SolveSchedule V;
   if (build_solve(c->P, c->S, V, c->rank, c->world, c->err)) return -1;
   for (int i = 0; i < 12; i++) out12[i] = 0;

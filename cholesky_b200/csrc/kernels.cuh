@@ -1,5 +1,5 @@
 // sm_100a kernels of the numeric factorization.  A handful of grouped kernels execute the whole level
-// schedule (see schedule.cc); one scatter kernel assembles A; two small kernels carry the multi-GPU
+// schedule (see schedule.cc); one scatter kernel assembles A; three small kernels carry the multi-GPU
 // exchange over NVLink peer memory.
 //
 //   gemm_grouped_ws  C -= sum_c A_c B_c^T on FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4),
@@ -7,17 +7,15 @@
 //                  (cp.async.bulk + mbarrier expect_tx), consumer warps issue the MMAs; one CTA per
 //                  destination tile, contributors accumulated in registers in a fixed order
 //                  (atomic-free, deterministic), lower-triangle masking for SYRK destinations.
-//                  SHARED variant: the tile is also stored into every peer's copy of the factor
-//                  (coalesced P2P stores), fusing the update with its broadcast.
 //                  Replaces cblas_dgemm / cblas_dsyrk as called at blas.rg:139-142, 187-189.
-//   gemm_grouped   the earlier cp.async version of the same kernel (CHOL_GEMM_WS=0).
 //   gemm_small_warp  the same update for small fronts: one warp per 32x32 tile, no shared memory.
-//   potrf_tile     Cholesky of one NB x NB pivot tile in shared memory, blocked by 16 columns
+//   potrf_tile     Cholesky of one NB x NB pivot tile, register-resident and right-looking
 //                  (LAPACKE_dpotrf, blas.rg:71).
 //   trsm_tile      one 128-row slab times L^-T by forward substitution, one row per thread
 //                  (cblas_dtrsm Right/Lower/Trans/NonUnit, blas.rg:99-100).
 //   assemble       factor[a_off[e]] = value[e]   (fill_block, mmat.rg:529-633).
-//   peer_barrier / allreduce_top   cross-GPU barrier and sum of the ranks' top-panel copies.
+//   push_rects / reduce_rects / peer_sync   rows of the top panels pushed to the peers' copies, partial
+//                  sums of the rows a rank owns pulled from its group, flag words in peer memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,135 +27,13 @@ namespace chb {
 constexpr int kMaxPeers = 8;
 struct Peers {
   double *fac[kMaxPeers];
-  unsigned long long *flags[kMaxPeers];
+  unsigned long long *flags[kMaxPeers];  // kFlagSlots x kMaxPeers words per rank: word (slot, source rank)
   int n, rank;
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  int bytes = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
 // D(8x8) += A(8x4, row) * B(4x8, col); lane = 4*g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-template <int BM, int BN, int BK, int WM, int WN, int STAGES>
-struct GemmCfg {
-  static constexpr int kWarpsM = BM / WM, kWarpsN = BN / WN;
-  static constexpr int kThreads = kWarpsM * kWarpsN * 32;
-  static constexpr int kPad = 4;  // row stride = 4 mod 16 doubles: conflict-free DMMA fragment loads
-  static constexpr int kLdA = BM + kPad, kLdB = BN + kPad;
-  static constexpr int kStageDoubles = BK * (kLdA + kLdB);
-  static constexpr int kSmemBytes = STAGES * kStageDoubles * 8;
-};
-
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool SHARED>
-__global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES>::kThreads)
-    gemm_grouped(const GemmProblem *__restrict__ probs, const GemmContrib *__restrict__ contribs,
-                 const TileRef *__restrict__ tiles, double *__restrict__ fac, Peers peers) {
-  using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES>;
-  extern __shared__ __align__(16) double smem[];
-  const TileRef tile = tiles[blockIdx.x];
-  const GemmProblem pr = probs[tile.prob];
-  const int row0 = tile.tr * BM, col0 = tile.tc * BN;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp % Cfg::kWarpsM) * WM, wn0 = (warp / Cfg::kWarpsM) * WN;
-  constexpr int MB = WM / 8, NBk = WN / 8;
-  double acc[MB][NBk][2];
-#pragma unroll
-  for (int i = 0; i < MB; i++)
-#pragma unroll
-    for (int j = 0; j < NBk; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  const int mrem = pr.M - row0, nrem = pr.N - col0;  // valid rows of A / B in this tile (may exceed BM/BN)
-
-  for (int c = 0; c < pr.contrib_count; c++) {
-    const GemmContrib cb = contribs[pr.contrib_begin + c];
-    const double *__restrict__ A = fac + cb.a_off + row0;
-    const double *__restrict__ Bp = fac + cb.b_off + col0;
-    const int K = cb.K, lda = cb.lda, ldb = cb.ldb;
-    const int nk = (K + BK - 1) / BK;
-
-    auto load_stage = [&](int stage, int kt) {
-      double *As = smem + stage * Cfg::kStageDoubles;
-      double *Bs = As + BK * Cfg::kLdA;
-      const int k0 = kt * BK;
-#pragma unroll
-      for (int i = tid; i < BK * (BM / 2); i += Cfg::kThreads) {
-        int kk = i / (BM / 2), m2 = (i % (BM / 2)) * 2;
-        bool ok = (m2 < mrem) && (k0 + kk < K);
-        cp_async16(As + kk * Cfg::kLdA + m2, ok ? (A + m2 + (size_t)(k0 + kk) * lda) : A, ok);
-      }
-#pragma unroll
-      for (int i = tid; i < BK * (BN / 2); i += Cfg::kThreads) {
-        int kk = i / (BN / 2), n2 = (i % (BN / 2)) * 2;
-        bool ok = (n2 < nrem) && (k0 + kk < K);
-        cp_async16(Bs + kk * Cfg::kLdB + n2, ok ? (Bp + n2 + (size_t)(k0 + kk) * ldb) : Bp, ok);
-      }
-    };
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-      if (s < nk) load_stage(s, s);
-      cp_async_commit();
-    }
-    for (int kt = 0; kt < nk; kt++) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      int nxt = kt + STAGES - 1;
-      if (nxt < nk) load_stage(nxt % STAGES, nxt);
-      cp_async_commit();
-      const double *As = smem + (kt % STAGES) * Cfg::kStageDoubles;
-      const double *Bs = As + BK * Cfg::kLdA;
-#pragma unroll
-      for (int k4 = 0; k4 < BK / 4; k4++) {
-        double a[MB], b[NBk];
-#pragma unroll
-        for (int i = 0; i < MB; i++) a[i] = As[(k4 * 4 + t) * Cfg::kLdA + wm0 + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < NBk; j++) b[j] = Bs[(k4 * 4 + t) * Cfg::kLdB + wn0 + j * 8 + g];
-#pragma unroll
-        for (int i = 0; i < MB; i++)
-#pragma unroll
-          for (int j = 0; j < NBk; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-  }
-
-  double *__restrict__ C = fac + pr.c_off;
-#pragma unroll
-  for (int i = 0; i < MB; i++) {
-    const int r = row0 + wm0 + i * 8 + g;
-    if (r >= pr.M) continue;
-#pragma unroll
-    for (int j = 0; j < NBk; j++) {
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
-        if (cc < pr.N && (!pr.tri || r >= cc)) {
-          const size_t o = r + (size_t)cc * pr.ldc;
-          const double v = C[o] - acc[i][j][e];
-          if (SHARED) {
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; p++)
-              if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
-          } else
-            C[o] = v;
-        }
-      }
-    }
-  }
-  if (SHARED) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,10 +85,10 @@ struct GemmWsCfg {
   static constexpr int kSmemBytes = STAGES * kStageDoubles * 8 + 2 * STAGES * 8 + STAGES * 4 + 64;
 };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool SHARED>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB>
 __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThreads, MINB)
     gemm_grouped_ws(const GemmProblem *__restrict__ probs, const GemmContrib *__restrict__ contribs,
-                    const TileRef *__restrict__ tiles, double *__restrict__ fac, Peers peers) {
+                    const TileRef *__restrict__ tiles, double *__restrict__ fac) {
   using Cfg = GemmWsCfg<BM, BN, BK, WM, WN, STAGES>;
   static_assert(BK * 2 <= 32 || BK == 32, "one bulk copy per producer lane");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -338,120 +214,33 @@ __global__ void __launch_bounds__(GemmWsCfg<BM, BN, BK, WM, WN, STAGES>::kThread
   }
 
   double *__restrict__ C = fac + pr.c_off;
-  if (!SHARED) {
-    // local destination: read-modify-write straight from the accumulator fragments (measured 2 % faster
-    // on one GPU than staging through shared memory).  All loads of one row block are issued before the
-    // first store: written as `C[..] -= acc` the compiler has to keep every store ahead of the next load
-    // (same array), i.e. 32 dependent round trips to L2/HBM per thread -- ncu's source view had 40 % of
-    // the warp samples of the K = 256 launches on those DADDs, and the DMMA pipe at 82 %.
+  // read-modify-write of the destination straight from the accumulator fragments.  All loads of one row
+  // block are issued before the first store: written as `C[..] -= acc` the compiler has to keep every store
+  // ahead of the next load (same array), i.e. 32 dependent round trips to L2/HBM per thread -- ncu's source
+  // view had 40 % of the warp samples of the K = 256 launches on those DADDs, and the DMMA pipe at 82 %.
+  const int rlo = (pr.tri & 2) ? 1 : 0;  // an ownership boundary on an odd row: row 0 belongs to the neighbour
+  const bool tri = pr.tri & 1;
 #pragma unroll
-    for (int i = 0; i < MB; i++) {
-      const int r = row0 + wm0 + i * 8 + g;
-      double cv[NBk][2];
-      bool ok[NBk][2];
-#pragma unroll
-      for (int j = 0; j < NBk; j++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int cc = col0 + wn0 + j * 8 + 2 * t + e;
-          ok[j][e] = r < pr.M && cc < pr.N && (!pr.tri || r >= cc);
-          cv[j][e] = ok[j][e] ? C[r + (size_t)cc * pr.ldc] : 0.0;
-        }
-#pragma unroll
-      for (int j = 0; j < NBk; j++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int cc = col0 + wn0 + j * 8 + 2 * t + e;
-          if (ok[j][e]) C[r + (size_t)cc * pr.ldc] = cv[j][e] - acc[i][j][e];
-        }
-    }
-    return;
-  }
-  // SHARED: the tile also goes to every peer's copy.  The accumulators are parked column-major in shared
-  // memory (stride BM + 2 keeps the fragment stores conflict-free), then every warp walks whole columns,
-  // lane = row, so the peer stores over NVLink are coalesced runs instead of 8-byte scatters.
-  constexpr int kLdC = BM + 2;
-  static_assert(BN * kLdC <= STAGES * Cfg::kStageDoubles, "C staging tile must fit in the stage ring");
-  asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kConsumers * 32) : "memory");  // all consumers are done with the ring
-  double *Cs = smem;
-#pragma unroll
-  for (int i = 0; i < MB; i++)
+  for (int i = 0; i < MB; i++) {
+    const int r = row0 + wm0 + i * 8 + g;
+    double cv[NBk][2];
+    bool ok[NBk][2];
 #pragma unroll
     for (int j = 0; j < NBk; j++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) Cs[(wn0 + j * 8 + 2 * t + e) * kLdC + wm0 + i * 8 + g] = acc[i][j][e];
-  asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kConsumers * 32) : "memory");
-  // 16-byte peer stores when every column of the tile starts on a 16-byte boundary (always true for the
-  // in-panel updates; Schur destinations start wherever their cluster starts)
-  const bool vec = (((pr.c_off + row0) | pr.ldc) & 1) == 0;
-  // Four columns per step: their loads of C go out together, then the peer stores.  One column at a time,
-  // every load had to wait for the previous column's stores (one of the peers is this rank's own copy).
-  constexpr int kColBatch = 4;
-  for (int jb = warp; jb < BN; jb += Cfg::kConsumers * kColBatch) {
-    if (col0 + jb >= pr.N) break;
-    if (vec) {
-#pragma unroll
-      for (int rr0 = 0; rr0 < BM; rr0 += 64) {
-        const int rr = rr0 + 2 * lane, r = row0 + rr;
-        double2 cv[kColBatch];
-        int okm[kColBatch];  // bit 0: row r is written, bit 1: row r + 1
-#pragma unroll
-        for (int u = 0; u < kColBatch; u++) {
-          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
-          const bool in = j < BN && cc < pr.N;
-          const bool ok0 = in && r < pr.M && (!pr.tri || r >= cc), ok1 = in && r + 1 < pr.M && (!pr.tri || r + 1 >= cc);
-          okm[u] = (ok0 ? 1 : 0) | (ok1 ? 2 : 0);
-          const size_t o = r + (size_t)cc * pr.ldc;
-          cv[u] = make_double2(0.0, 0.0);
-          if (okm[u] == 3) cv[u] = *reinterpret_cast<const double2 *>(C + o);
-          else if (okm[u] == 1) cv[u].x = C[o];
-          else if (okm[u] == 2) cv[u].y = C[o + 1];
-        }
-#pragma unroll
-        for (int u = 0; u < kColBatch; u++) {
-          if (!okm[u]) continue;
-          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
-          const size_t o = r + (size_t)cc * pr.ldc;
-          const double2 v = make_double2(cv[u].x - Cs[j * kLdC + rr], cv[u].y - Cs[j * kLdC + rr + 1]);
-          if (okm[u] == 3) {
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; p++)
-              if (p < peers.n) *reinterpret_cast<double2 *>(peers.fac[p] + pr.c_off + o) = v;
-          } else {
-            const int q = okm[u] == 1 ? 0 : 1;
-            const double w = q ? v.y : v.x;
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; p++)
-              if (p < peers.n) peers.fac[p][pr.c_off + o + q] = w;
-          }
-        }
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+        ok[j][e] = r >= rlo && r < pr.M && cc < pr.N && (!tri || r >= cc);
+        cv[j][e] = ok[j][e] ? C[r + (size_t)cc * pr.ldc] : 0.0;
       }
-    } else {
 #pragma unroll
-      for (int rr0 = 0; rr0 < BM; rr0 += 32) {
-        const int rr = rr0 + lane, r = row0 + rr;
-        double cv[kColBatch];
-        bool ok[kColBatch];
+    for (int j = 0; j < NBk; j++)
 #pragma unroll
-        for (int u = 0; u < kColBatch; u++) {
-          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
-          ok[u] = j < BN && cc < pr.N && r < pr.M && (!pr.tri || r >= cc);
-          cv[u] = ok[u] ? C[r + (size_t)cc * pr.ldc] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < kColBatch; u++) {
-          if (!ok[u]) continue;
-          const int j = jb + u * Cfg::kConsumers, cc = col0 + j;
-          const size_t o = r + (size_t)cc * pr.ldc;
-          const double v = cv[u] - Cs[j * kLdC + rr];
-#pragma unroll
-          for (int p = 0; p < kMaxPeers; p++)
-            if (p < peers.n) peers.fac[p][pr.c_off + o] = v;
-        }
+      for (int e = 0; e < 2; e++) {
+        const int cc = col0 + wn0 + j * 8 + 2 * t + e;
+        if (ok[j][e]) C[r + (size_t)cc * pr.ldc] = cv[j][e] - acc[i][j][e];
       }
-    }
   }
-  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -512,7 +301,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmPr
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int cc = col0 + j * 8 + 2 * t + e;
-        ok[j][e] = r < pr.M && cc < pr.N && (!pr.tri || r >= cc);
+        ok[j][e] = r >= ((pr.tri >> 1) & 1) && r < pr.M && cc < pr.N && (!(pr.tri & 1) || r >= cc);
         cv[j][e] = ok[j][e] ? C[r + (size_t)cc * pr.ldc] : 0.0;
       }
 #pragma unroll
@@ -528,187 +317,6 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmPr
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 64;
 
-// Pivot tile in shared memory (row stride 65: conflict-free), blocked by 16 columns.  Inside a block:
-// left-looking by column with one thread per row (64 threads, named barrier) -- all rows at or below
-// the diagonal take their short dot product with row k at once, thread k turns its result into
-// 1/sqrt, the others scale.  After a block: rank-16 update of the trailing lower triangle by all 256
-// threads.  Compact loops on purpose: a fully unrolled version is instruction-fetch bound.
-constexpr int kPotrfThreads = 256;
-constexpr int kPB = 16;
-__global__ void __launch_bounds__(kPotrfThreads) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
-                                                            int *__restrict__ info) {
-  __shared__ double T[kNB][kNB + 1];
-  __shared__ double rk;  // 1 / L[k][k]
-  const PotrfDesc d = descs[blockIdx.x];
-  double *__restrict__ A = fac + d.off;
-  const int nb = d.nb, tid = threadIdx.x;
-  {  // thread (row i, column group cg) loads 16 columns, eight loads in flight
-    const int i = tid & (kNB - 1), cg = tid / kNB;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int c = cg * 16 + h * 8 + u;
-        v[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) T[i][cg * 16 + h * 8 + u] = v[u];
-    }
-  }
-  __syncthreads();
-  for (int kb = 0; kb < nb; kb += kPB) {
-    const int kend = min(kb + kPB, nb);
-    if (tid < kNB) {
-      const int i = tid;
-      for (int k = kb; k < kend; k++) {
-        double sk = 0.0;
-        if (i >= k && i < nb) {
-          double s0 = T[i][k], s1 = 0.0;
-          int j = kb;
-          for (; j + 3 < k; j += 4) {
-            const double a0 = T[i][j], a1 = T[i][j + 1], a2 = T[i][j + 2], a3 = T[i][j + 3];
-            const double b0 = T[k][j], b1 = T[k][j + 1], b2 = T[k][j + 2], b3 = T[k][j + 3];
-            s0 -= a0 * b0, s1 -= a1 * b1, s0 -= a2 * b2, s1 -= a3 * b3;
-          }
-          for (; j < k; j++) s0 -= T[i][j] * T[k][j];
-          sk = s0 + s1;
-        }
-        if (i == k) {
-          if (!(sk > 0.0)) {
-            atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-            sk = 1.0;
-          }
-          const double r = rsqrt(sk);
-          T[k][k] = sk * r;
-          rk = r;
-        }
-        asm volatile("bar.sync 1, 64;\n" ::: "memory");
-        if (i > k && i < nb) T[i][k] = sk * rk;
-        asm volatile("bar.sync 1, 64;\n" ::: "memory");
-      }
-    }
-    __syncthreads();
-    const int rem = nb - kend;
-    if (rem > 0) {  // T[i][j] -= sum_k T[i][k] T[j][k] over the block just factored, i >= j >= kend
-      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
-        const int i = kend + idx % rem, j = kend + idx / rem;
-        if (i < j) continue;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-        for (int k = kb; k < kend; k += 2) {
-          s0 += T[i][k] * T[j][k];
-          if (k + 1 < kend) s1 += T[i][k + 1] * T[j][k + 1];
-        }
-        T[i][j] -= s0 + s1;
-      }
-    }
-    __syncthreads();
-  }
-  {
-    const int i = tid & (kNB - 1), cg = tid / kNB;
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int c = cg * 16 + u;
-      if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = T[i][c];
-    }
-  }
-}
-
-// potrf_tile_w: same tile, but the column steps are done by ONE warp (two rows per lane) so that the 64
-// dependent steps synchronise with __syncwarp and a shuffle instead of block barriers and a round trip
-// through shared memory; every lane computes the pivot's 1/sqrt itself.  Blocks of 8 columns keep the
-// in-block dot products short; the rank-8 trailing update uses all 256 threads.
-constexpr int kPB2 = 8;
-__global__ void __launch_bounds__(kPotrfThreads) potrf_tile_w(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
-                                                              int *__restrict__ info) {
-  __shared__ double T[kNB][kNB + 1];
-  const PotrfDesc d = descs[blockIdx.x];
-  double *__restrict__ A = fac + d.off;
-  const int nb = d.nb, tid = threadIdx.x, lane = tid & 31;
-  {
-    const int i = tid & (kNB - 1), cg = tid / kNB;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int c = cg * 16 + h * 8 + u;
-        v[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) T[i][cg * 16 + h * 8 + u] = v[u];
-    }
-  }
-  __syncthreads();
-  for (int kb = 0; kb < nb; kb += kPB2) {
-    const int kend = min(kb + kPB2, nb);
-    if (tid < 32) {
-      const int r0 = lane, r1 = lane + 32;
-      for (int k = kb; k < kend; k++) {
-        double s0 = 0.0, s1 = 0.0;
-        if (r0 >= k && r0 < nb) s0 = T[r0][k];
-        if (r1 >= k && r1 < nb) s1 = T[r1][k];
-        for (int j = kb; j < k; j++) {
-          const double b = T[k][j];
-          s0 -= T[r0][j] * b;  // rows above the diagonal or beyond nb compute garbage that is never stored
-          s1 -= T[r1][j] * b;
-        }
-        double sk = __shfl_sync(0xffffffffu, k < 32 ? s0 : s1, k & 31);
-        if (!(sk > 0.0)) {
-          if (lane == 0) atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-          sk = 1.0;
-        }
-        // 1/sqrt from the single-precision seed and two Newton steps in double (error ~2 ulp); the
-        // library routine's longer dependent chain sits on the critical path of all 64 columns
-        double r;
-        if (sk > 1e-30 && sk < 1e30) {
-          r = (double)rsqrtf((float)sk);
-          const double hs = 0.5 * sk;
-          r = r * (1.5 - hs * r * r);
-          r = r * (1.5 - hs * r * r);
-        } else
-          r = rsqrt(sk);
-        if (r0 == k || r1 == k) T[k][k] = sk * r;
-        if (r0 > k && r0 < nb) T[r0][k] = s0 * r;
-        if (r1 > k && r1 < nb) T[r1][k] = s1 * r;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    const int rem = nb - kend;
-    if (rem > 0) {
-      for (int idx = tid; idx < rem * rem; idx += kPotrfThreads) {
-        const int i = kend + idx % rem, j = kend + idx / rem;
-        if (i < j) continue;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-        for (int k = kb; k < kend; k += 2) {
-          s0 += T[i][k] * T[j][k];
-          if (k + 1 < kend) s1 += T[i][k + 1] * T[j][k + 1];
-        }
-        T[i][j] -= s0 + s1;
-      }
-    }
-    __syncthreads();
-  }
-  {
-    const int i = tid & (kNB - 1), cg = tid / kNB;
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int c = cg * 16 + u;
-      if (i < nb && c <= i && c < nb) A[i + (size_t)c * d.ld] = T[i][c];
-    }
-  }
-}
-
-// potrf_tile_r (EXPERIMENTAL, CHOL_POTRF_R=1; parity-checked on one fixture, 2 % faster only: it spills): the same tile, right-looking and
-// register-resident.  64 threads, thread i holds row i of the tile (64 doubles).  Step k: every thread
-// publishes its entry of column k (unscaled) in shared memory, one barrier, then a_ij -= (a_ik / a_kk) a_jk
-// for the rest of its row and a_ik *= 1/sqrt(a_kk).  One barrier and one rsqrt per column step instead of the
-// blocked dot products of potrf_tile_w (1 140 cycles per column): the step is ~60 dependent cycles of
-// arithmetic plus the barrier.  Entries above the diagonal carry finite garbage that is never stored.
-constexpr int kPotrfRThreads = kNB;
 __device__ __forceinline__ double rsqrt_newton(double s) {
   // 1/sqrt from the single-precision seed and two Newton steps in double (~2 ulp), as in potrf_tile_w
   if (s > 1e-30 && s < 1e30) {
@@ -719,58 +327,16 @@ __device__ __forceinline__ double rsqrt_newton(double s) {
   }
   return rsqrt(s);
 }
-__global__ void __launch_bounds__(kPotrfRThreads) potrf_tile_r(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
-                                                               int *__restrict__ info) {
-  __shared__ __align__(16) double colbuf[2][kNB];
-  const PotrfDesc d = descs[blockIdx.x];
-  double *__restrict__ A = fac + d.off;
-  const int i = threadIdx.x, nb = d.nb;
-  double a[kNB];
-  // rows and columns beyond nb are an identity block: their steps are no-ops
-#pragma unroll
-  for (int c = 0; c < kNB; c++) a[c] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : ((c == i && i >= nb) ? 1.0 : 0.0);
-#pragma unroll
-  for (int k = 0; k < kNB; k++) {
-    double *cb = colbuf[k & 1];  // double-buffered: a thread is at most one step ahead of the slowest one
-    cb[i] = a[k];
-    __syncthreads();
-    double p = cb[k];
-    if (!(p > 0.0)) {
-      if (i == k) atomicMin(info, d.col0 + k + 1);  // 1-based permuted column of the first bad pivot
-      p = 1.0;
-    }
-    const double r = rsqrt_newton(p);
-    const double t = a[k] * (r * r);
-    a[k] *= r;
-    int j = k + 1;
-    if (j & 1) {
-      if (j < kNB) a[j] -= t * cb[j];
-      j++;
-    }
-#pragma unroll
-    for (; j < kNB; j += 2) {
-      const double2 c2 = *reinterpret_cast<const double2 *>(&cb[j]);
-      a[j] -= t * c2.x;
-      a[j + 1] -= t * c2.y;
-    }
-  }
-  if (i < nb) {
-#pragma unroll
-    for (int c = 0; c < kNB; c++)
-      if (c <= i) A[i + (size_t)c * d.ld] = a[c];
-  }
-}
-
-// potrf_tile_r2 (EXPERIMENTAL, CHOL_POTRF_R=2; parity-checked on one fixture, pivot-tile time of 64^3 5.97 -> 4.90 ms,
-// profiles/experimental_variants_r01.md; off by default until the whole GPU suite has run with it): potrf_tile_r with each row split over
-// two threads (columns 0-31 in warps 0-1, columns 32-63 in warps 2-3): 32 doubles per thread instead of 64,
-// no register spills.  The two halves run different (warp-uniform) code and meet at one named barrier per step.
+// potrf_tile: 64 x 64 pivot tile, right-looking and register-resident.  128 threads, thread (i, h) holds columns
+// 32h .. 32h+31 of row i.  Step k: the owners of column k publish it (unscaled) in shared memory, one named
+// barrier, then a_ij -= (a_ik / a_kk) a_jk for the rest of the row and a_ik *= 1/sqrt(a_kk).  One barrier and one
+// rsqrt per column step; the two halves run different (warp-uniform) code.  Entries above the diagonal carry
+// finite garbage that is never stored.  (Measured against the shared-memory left-looking versions of round 1:
+// pivot-tile time of 64^3 5.98 -> 5.03 ms, profiles/experimental_variants_r02.md.)
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-// MINB = 1: 254 registers (the measured build); MINB = 3: 168 registers, no spills, three CTAs per SM for the
-// launches with thousands of tiles at the bottom of the tree (CHOL_POTRF_R=3, not measured yet).
-template <int MINB>
-__global__ void __launch_bounds__(2 * kNB, MINB) potrf_tile_r2(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
-                                                         int *__restrict__ info) {
+constexpr int kPotrfThreads = 2 * kNB;
+__global__ void __launch_bounds__(kPotrfThreads) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
+                                                            int *__restrict__ info) {
   __shared__ __align__(16) double colbuf[2][kNB];
   const PotrfDesc d = descs[blockIdx.x];
   double *__restrict__ A = fac + d.off;
@@ -847,10 +413,8 @@ __global__ void __launch_bounds__(2 * kNB, MINB) potrf_tile_r2(const PotrfDesc *
 // unrolled: the straight-line version was instruction-fetch bound.
 constexpr int kSlab = 128;
 constexpr int kTrsmSmemBytes = (kNB * kNB + kNB + kNB * kSlab) * 8;
-// BATCH (EXPERIMENTAL, CHOL_TRSM_BATCH=1; parity-checked on one fixture, trsm time of 64^3 4.06 -> 3.47 ms,
-// profiles/experimental_variants_r01.md; off by default until the whole GPU suite has run with it): all 64
-// column loads of the slab row in flight at once instead of eight rounds of eight.
-template <bool BATCH>
+// All 64 column loads of a slab row are in flight at once (measured: trsm time of 64^3 4.04 -> 3.50 ms against
+// eight rounds of eight).
 __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
                                                    double *__restrict__ fac) {
   extern __shared__ __align__(16) double tsm[];
@@ -865,20 +429,12 @@ __global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ 
   const int row = slab * kSlab + tid;
   const bool live = row < d.rows;
   double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
-  if (BATCH) {
+  {
     double v[kNB];
 #pragma unroll
     for (int c = 0; c < kNB; c++) v[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
 #pragma unroll
     for (int c = 0; c < kNB; c++) xs[c][tid] = v[c];
-  } else {
-    for (int c0 = 0; c0 < nb8; c0 += 8) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = (live && c0 + u < nb) ? Bp[(size_t)(c0 + u) * d.ld] : 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; u++) xs[c0 + u][tid] = v[u];
-    }
   }
   {
     constexpr int PER = kNB * kNB / kSlab;
@@ -941,55 +497,120 @@ __global__ void gather_diag_kernel(const int64_t *__restrict__ diag_off, int n, 
   if (i < n) out[i] = fac[diag_off[i]];
 }
 
+
 // ---------------------------------------------------------------------------------------------
-// Cross-GPU barrier over peer-mapped flag words: every rank publishes `epoch` into its slot of every
-// peer's flag array, then waits until all peers have published theirs.  One kernel per GPU, each
-// GPU runs its own process's kernel, so the waits cannot starve each other.
-__global__ void peer_barrier(Peers peers, unsigned long long epoch) {
+// Multi-GPU exchange over NVLink peer memory.  Every rank maps every peer's factor buffer and flag words
+// (CUDA IPC between processes, plain peer access inside one process).  Flag word (slot, s) of rank r is
+// written only by rank s and only with growing values; a waiter spins with acquire loads on its own words.
+// A wait gives up after kSpinLimit cycles (or as soon as another wait of this GPU has given up) and raises
+// *err, so a lost peer turns into an error code instead of a hung GPU.
+constexpr long long kSpinLimit = 20000000000LL;  // ~10 s at 2 GHz
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// lane p: raise word (slot, me) of rank p if p is in sig, then wait for own word (slot, p) if p is in wait
+__device__ __forceinline__ void signal_and_wait(const Peers &peers, int slot, unsigned long long value, unsigned sig, unsigned wait, int *err) {
   const int p = threadIdx.x;
-  __threadfence_system();
-  if (p < peers.n) {
-    unsigned long long *dst = peers.flags[p] + peers.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(dst), "l"(epoch) : "memory");
-    const unsigned long long *src = peers.flags[peers.rank] + p;
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(src) : "memory");
-    } while (v < epoch);
+  if (p < peers.n && ((sig >> p) & 1u)) st_release_sys(peers.flags[p] + slot * kMaxPeers + peers.rank, value);
+  if (p < peers.n && ((wait >> p) & 1u)) {
+    const unsigned long long *src = peers.flags[peers.rank] + slot * kMaxPeers + p;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(src) < value) {
+      if (*reinterpret_cast<volatile int *>(err) != 0 || clock64() - t0 > kSpinLimit) {
+        atomicExch(err, 1);
+        break;
+      }
+    }
   }
-  __syncthreads();
+}
+__global__ void __launch_bounds__(32) peer_sync(Peers peers, int slot, unsigned long long value, unsigned sig, unsigned wait, int *err) {
+  __threadfence_system();
+  signal_and_wait(peers, slot, value, sig, wait, err);
+  __syncwarp();
   __threadfence_system();
 }
 
-// Sum of all ranks' copies of the top panels: rank r reduces slice r (peer loads over NVLink, fixed
-// summation order, so every rank ends with bit-identical values) and stores the sums into every
-// copy (peer stores).  Bracketed by peer_barrier on both sides.
-// One panel per launch (off2 / n2 in double2 units, ld2 = ld / 2, npiv = pivot-block columns): chunks of
-// 4096 double2 go round-robin to the ranks; only the ranks in `mask` hold contributions (the others'
-// copies are still zero), and elements strictly above the pivot block's diagonal are never touched by
-// the factorization, so they are skipped.
-constexpr int kArChunk = 4096;
-__global__ void __launch_bounds__(256) allreduce_top(Peers peers, int64_t off2, int64_t n2, int ld2, int npiv, unsigned mask) {
-  const int64_t nchunks = (n2 + kArChunk - 1) / kArChunk;
-  for (int64_t ch = (int64_t)blockIdx.x * peers.n + peers.rank; ch < nchunks; ch += (int64_t)gridDim.x * peers.n) {
-    for (int64_t i = ch * kArChunk + threadIdx.x; i < min(n2, (ch + 1) * kArChunk); i += blockDim.x) {
-      const int64_t col = i / ld2;
-      const int64_t row = (i - col * ld2) * 2;
-      if (col < npiv && row + 1 < col) continue;
-      const int64_t gi = off2 + i;
+// push_rects: rectangle d (rows x cols, column-major, leading dimension ld, first entry at fac + off) is stored
+// at the same offset into the factor buffer of every rank in `mask`.  One CTA per (rectangle, group of
+// kPushCols columns); rows move as 16-byte pairs (offsets and leading dimensions are even, a trailing odd row
+// takes its padding neighbour along).  tri0 < kNoTriDev: entries with column > tri0 + row are skipped (the
+// strictly upper part of a diagonal block).  The last CTA to finish raises flag (slot, me) of the ranks in sig.
+constexpr int kPushCols = 32, kPushThreads = 256;
+constexpr int kNoTriDev = 1 << 29;
+__global__ void __launch_bounds__(kPushThreads) push_rects(const RectDesc *__restrict__ rects, double *__restrict__ fac, Peers peers, unsigned mask,
+                                                           int slot, unsigned long long value, unsigned sig, unsigned *__restrict__ counter) {
+  const RectDesc d = rects[blockIdx.x / (kRowBlock / kPushCols)];
+  const int cg = blockIdx.x % (kRowBlock / kPushCols);
+  const int rows2 = (d.rows + 1) / 2;
+  for (int c = cg * kPushCols + (int)threadIdx.x / 128; c < min(d.cols, (cg + 1) * kPushCols); c += kPushThreads / 128) {
+    for (int r2 = threadIdx.x % 128; r2 < rows2; r2 += 128) {
+      if (d.tri0 < kNoTriDev && c > d.tri0 + 2 * r2 + 1) continue;
+      const int64_t o = d.off + 2 * r2 + (int64_t)c * d.ld;
+      const double2 v = *reinterpret_cast<const double2 *>(fac + o);
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; p++)
+        if (p < peers.n && ((mask >> p) & 1u)) *reinterpret_cast<double2 *>(peers.fac[p] + o) = v;
+    }
+  }
+  if (!sig) return;
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *counter = 0;
+  __threadfence_system();
+  if (threadIdx.x < 32) signal_and_wait(peers, slot, value, sig, 0u, nullptr);
+}
+
+// reduce_rects: for every rectangle (rows this rank owns of a top panel) the partial sums held by the ranks in
+// `mask` (its group, itself included) are added in ascending rank order and stored into this rank's copy.
+__global__ void __launch_bounds__(kPushThreads) reduce_rects(const RectDesc *__restrict__ rects, double *__restrict__ fac, Peers peers, unsigned mask,
+                                                             int col_groups) {
+  const RectDesc d = rects[blockIdx.x / col_groups];
+  const int cg = blockIdx.x % col_groups;
+  const int rows2 = (d.rows + 1) / 2;
+  const int cpg = (d.cols + col_groups - 1) / col_groups;
+  for (int c = cg * cpg + (int)threadIdx.x / 128; c < min(d.cols, (cg + 1) * cpg); c += kPushThreads / 128) {
+    for (int r2 = threadIdx.x % 128; r2 < rows2; r2 += 128) {
+      if (d.tri0 < kNoTriDev && c > d.tri0 + 2 * r2 + 1) continue;
+      const int64_t o = d.off + 2 * r2 + (int64_t)c * d.ld;
       double2 s = make_double2(0.0, 0.0);
 #pragma unroll
       for (int p = 0; p < kMaxPeers; p++)
         if (p < peers.n && ((mask >> p) & 1u)) {
-          const double2 v = reinterpret_cast<const double2 *>(peers.fac[p])[gi];
+          const double2 v = *reinterpret_cast<const double2 *>(peers.fac[p] + o);
           s.x += v.x, s.y += v.y;
         }
-#pragma unroll
-      for (int p = 0; p < kMaxPeers; p++)
-        if (p < peers.n) reinterpret_cast<double2 *>(peers.fac[p])[gi] = s;
+      *reinterpret_cast<double2 *>(fac + o) = s;
     }
   }
-  __threadfence_system();
+}
+
+// compare_rects: largest |difference| between this rank's copy of the rectangles and the copy of rank `peer`
+// (verification of the claim that every rank ends with identical top panels); the result is the bit pattern of a
+// non-negative double, so an integer atomicMax orders it.
+__global__ void __launch_bounds__(kPushThreads) compare_rects(const RectDesc *__restrict__ rects, const double *__restrict__ fac, Peers peers, int peer,
+                                                              int col_groups, unsigned long long *__restrict__ worst) {
+  const RectDesc d = rects[blockIdx.x / col_groups];
+  const int cg = blockIdx.x % col_groups;
+  const int cpg = (d.cols + col_groups - 1) / col_groups;
+  const double *__restrict__ other = peers.fac[peer];
+  double w = 0.0;
+  for (int c = cg * cpg + (int)threadIdx.x / 128; c < min(d.cols, (cg + 1) * cpg); c += kPushThreads / 128)
+    for (int r = threadIdx.x % 128; r < d.rows; r += 128) {
+      if (d.tri0 < kNoTriDev && c > d.tri0 + r) continue;
+      const int64_t o = d.off + r + (int64_t)c * d.ld;
+      const double df = fabs(fac[o] - other[o]);
+      w = fmax(w, (df == df) ? df : 1e300);  // a NaN on either side counts as a difference
+    }
+  if (w > 0.0) atomicMax(worst, (unsigned long long)__double_as_longlong(w));
 }
 
 }  // namespace chb

@@ -17,13 +17,22 @@
 // a second stream.  The trailing update of block column J is split into the tiles of block column
 // J + 1 (part A) and the rest (part B); the chain of J + 1 only waits for A, so it overlaps B.
 //
-// Multi-GPU (world = 2^d ranks, one process per GPU): rank r owns the subtree under heap index
-// 2^d + r and schedules only its separators on levels >= d.  Its Schur contributions to the top
-// d levels land in its own copy of the top panels; one K_ALLREDUCE sums the copies over NVLink.
-// On the top levels every rank runs the chain redundantly (bit-identical).  Trailing updates use a
-// static ownership of tile rows (row tile index mod world): part A is stored into every rank's
-// copy (SHARED kernel) and followed by a K_BARRIER, part B stays local until its block column's turn.
-// Schur updates of top levels are split by contiguous tile slices and stored into every copy.
+// Multi-GPU (world = 2^d ranks, one per GPU): rank r owns the subtree under heap index 2^d + r and
+// schedules only its separators on levels >= d.  Its Schur contributions to the top d levels land in
+// its own copy of the top panels (partial sums).  Every top panel belongs to the group of ranks under
+// it and its stored rows are dealt to them in blocks of 256 (TopGroup, chol_internal.h); from then on
+// the owner of a row computes it and nobody else does:
+//   * after level d one K_REDUCE per rank sums the group's partial sums of the rows it owns (peer loads);
+//   * per 256-wide block column J of a top panel: the owner of the diagonal block factors it and pushes
+//     it to every rank (peer stores + flag SLOT_DIAG); every rank of the group solves its own rows
+//     below it, pushes the pivot-block part of them to the group (flag SLOT_GROUP, the trailing update
+//     needs them as its B operand) and, on a background stream, everything else to everybody; then
+//     each rank updates its own rows of the trailing matrix (parts A / B as above);
+//   * after a top level a world barrier (all pushed rows have landed: every rank now holds the complete
+//     factored panels of the level), then its Schur updates, each destination row block computed by
+//     its owner from its local copies.
+// Every entry of the factor is computed by exactly one rank and copied, so all copies of the top
+// panels end bit-identical.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +43,8 @@ namespace chb {
 
 namespace {
 
+constexpr int kNoTri = 1 << 30;
+
 struct Builder {
   const Problem &P;
   const Symbolic &S;
@@ -41,12 +52,13 @@ struct Builder {
   Builder(const Problem &p, const Symbolic &s, Schedule &d) : P(p), S(s), D(d) {}
 
   // ---- launches, streams and events
-  int last[2] = {-1, -1};   // index of the last launch pushed on each stream
-  int pendw[2] = {-1, -1};  // event the next launch of the stream has to wait for
-  static Launch mk(int kind, int level, int phase, int64_t begin, int64_t count, double flops, int cfg, int shared) {
+  int last[3] = {-1, -1, -1};   // index of the last launch pushed on each stream
+  int pendw[3] = {-1, -1, -1};  // event the next launch of the stream has to wait for
+  static Launch mk(int kind, int level, int phase, int64_t begin = 0, int64_t count = 0, double flops = 0, int cfg = 0) {
     Launch l;
-    l.kind = kind, l.level = level, l.phase = phase, l.begin = begin, l.count = count, l.flops = flops, l.cfg = cfg, l.shared = shared;
+    l.kind = kind, l.level = level, l.phase = phase, l.begin = begin, l.count = count, l.flops = flops, l.cfg = cfg;
     l.stream = 0, l.wait_ev = -1, l.rec_ev = -1;
+    l.mask = l.sig_mask = l.wait_mask = 0, l.slot = 0, l.seq = 0;
     return l;
   }
   void push(Launch l, int stream) {
@@ -62,36 +74,37 @@ struct Builder {
     if (!D.lookahead || dst == src || last[src] < 0) return;
     if (D.launches[last[src]].rec_ev < 0) D.launches[last[src]].rec_ev = D.num_events++;
     const int ev = D.launches[last[src]].rec_ev;
-    if (pendw[dst] >= 0 && pendw[dst] != ev) push(mk(K_NOP, D.launches[last[src]].level, 0, 0, 0, 0, 0, 0), dst);
+    if (pendw[dst] >= 0 && pendw[dst] != ev) push(mk(K_NOP, D.launches[last[src]].level, 0), dst);
     pendw[dst] = ev;
+  }
+  void sync(int level, int phase, int slot, int64_t seq, unsigned sig, unsigned wait, int stream) {
+    Launch l = mk(K_SYNC, level, phase);
+    l.slot = slot, l.seq = seq, l.sig_mask = sig, l.wait_mask = wait;
+    push(l, stream);
+  }
+  // rectangles [begin, D.rects.size()) go to the ranks in `mask`; then flag (slot, me) of `sig` rises to seq
+  void push_rects(int level, int phase, int64_t begin, unsigned mask, int slot, int64_t seq, unsigned sig, int stream) {
+    Launch l = mk(K_PUSH, level, phase, begin, (int64_t)D.rects.size() - begin);
+    l.mask = mask, l.slot = slot, l.seq = seq, l.sig_mask = sig;
+    if (l.count > 0 || sig) push(l, stream);
   }
 
   // ---- grouped GEMM launches
   struct Pending {
     int prob;
     double flops;
-    // trailing update of a panel: tile rows are owned by rank (row_tile0 + tr) % world for the whole
-    // panel factorization; tile columns < bcast_tc belong to the next block column (part A)
+    // trailing update of a panel (mode 1): tile row tr of the problem is tile row row_tile0 + tr of the
+    // panel; tile columns < bcast_tc belong to the next block column (part A)
     int row_tile0 = -1, bcast_tc = 0;
   };
   std::vector<Pending> pend;
-  int mode = 0;  // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = NB)
+  int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = NB)
+  const TopGroup *own = nullptr;  // mode 1 on a top panel: only the tile rows this rank owns
   void begin_gemm(int m) {
     pend.clear();
     mode = m;
   }
-  bool is_big(const GemmProblem &g) const { return g.M >= D.big_m && g.N >= D.big_n; }
-  static int cfg_bm(int cfg) { return cfg == 3 ? 32 : cfg == 0 ? 64 : 128; }
-  static int cfg_bn(int cfg) { return cfg == 3 ? 32 : cfg == 1 ? 128 : 64; }
-  static int64_t ntiles(const GemmProblem &g, int cfg) {
-    const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
-    int64_t tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
-    if (!g.tri) return tr_n * tc_n;
-    int64_t t = 0;
-    for (int64_t tc = 0; tc < tc_n; tc++)
-      for (int64_t tr = 0; tr < tr_n; tr++) t += !((tr + 1) * bm - 1 < tc * bn);
-    return t;
-  }
+  static double gemm_flops(int M, int N, int K, int tri) { return 2.0 * K * ((double)M * N - ((tri & 1) ? 0.5 * N * (N - 1.0) : 0.0)); }
   // one problem with a single contributor (in-panel updates)
   void add_problem(int64_t c_off, int ldc, int M, int N, int tri, int64_t a_off, int64_t b_off, int lda, int ldb, int K,
                    int row_tile0 = -1, int bcast_tc = 0) {
@@ -103,22 +116,18 @@ struct Builder {
     D.probs.push_back(g);
     Pending pd;
     pd.prob = (int)D.probs.size() - 1;
-    // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
-    pd.flops = 2.0 * K * ((double)M * N - (tri ? 0.5 * N * (N - 1.0) : 0.0));
+    pd.flops = gemm_flops(M, N, K, tri);  // executed flops: the strict upper triangle of the leading N x N part is skipped when tri
     pd.row_tile0 = row_tile0, pd.bcast_tc = bcast_tc;
     pend.push_back(pd);
   }
-  void push_gemm(int level, int phase, int cfg, int64_t begin, int64_t count, double flops, int shared, int stream) {
-    if (count > 0 || shared == 1) push(mk(K_GEMM, level, phase, begin, count, flops, cfg, shared), stream);
-    if (shared == 1) push(mk(K_BARRIER, level, phase, 0, 0, 0, 0, 0), stream);
+  void push_gemm(int level, int phase, int cfg, int64_t begin, int64_t count, double flops, int stream) {
+    if (count > 0) push(mk(K_GEMM, level, phase, begin, count, flops, cfg), stream);
   }
-  void emit(int level, int phase, int cfg, const std::vector<Pending> &list, bool top) {
+  void emit(int level, int phase, int cfg, const std::vector<Pending> &list) {
     if (list.empty()) return;
-    const int bm = cfg_bm(cfg), bn = cfg_bn(cfg);
-    const bool multi = top && D.world > 1;
-    if (mode == 1 && cfg == 0) {
-      // part A: the next block column's tiles (in multi-GPU mode stored into every rank's copy);
-      // part B: the rest of the trailing panel (local).  Tile rows have a static owner.
+    const int bm = cfg == 3 ? 32 : 64, bn = bm;
+    if (mode == 1) {
+      // part A: the next block column's tiles; part B: the rest of the trailing panel
       double all_tiles = 0, flops = 0;
       std::vector<TileRef> pa, pb;
       for (const Pending &pd : list) {
@@ -126,9 +135,9 @@ struct Builder {
         int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
         for (int tc = 0; tc < tc_n; tc++)
           for (int tr = 0; tr < tr_n; tr++) {
-            if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;
+            if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;
             all_tiles += 1;
-            if (multi && (pd.row_tile0 + tr) % D.world != D.rank) continue;
+            if (own && own->owner((pd.row_tile0 + tr) * bm / own->rb) != D.rank) continue;
             (tc < pd.bcast_tc ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
           }
         flops += pd.flops;
@@ -137,11 +146,11 @@ struct Builder {
       depend(0, 1);  // the chain of this block column is done
       int64_t b0 = (int64_t)D.tiles.size();
       D.tiles.insert(D.tiles.end(), pa.begin(), pa.end());
-      push_gemm(level, phase, cfg, b0, (int64_t)pa.size(), per_tile * (double)pa.size(), multi ? 1 : 0, 0);
+      push_gemm(level, phase, cfg, b0, (int64_t)pa.size(), per_tile * (double)pa.size(), 0);
       depend(1, 0);  // the next chain may start as soon as part A is in place
       int64_t b1 = (int64_t)D.tiles.size();
       D.tiles.insert(D.tiles.end(), pb.begin(), pb.end());
-      push_gemm(level, phase, cfg, b1, (int64_t)pb.size(), per_tile * (double)pb.size(), multi ? 2 : 0, 0);
+      push_gemm(level, phase, cfg, b1, (int64_t)pb.size(), per_tile * (double)pb.size(), 0);
       return;
     }
     int64_t begin = (int64_t)D.tiles.size();
@@ -151,44 +160,27 @@ struct Builder {
       int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
       for (int tc = 0; tc < tc_n; tc++)
         for (int tr = 0; tr < tr_n; tr++) {
-          if (g.tri && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
+          if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
           D.tiles.push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
         }
       flops += pd.flops;
     }
-    int64_t count = (int64_t)D.tiles.size() - begin;
-    int shared = 0;
-    if (multi && mode != 2 && flops >= D.shared_min_flops) {
-      // split the tile list across the ranks; every rank builds the same list, keeps its slice
-      int64_t lo = count * D.rank / D.world, hi = count * (D.rank + 1) / D.world;
-      flops *= (double)(hi - lo) / (double)std::max<int64_t>(1, count);
-      begin += lo, count = hi - lo;
-      shared = 1;
-    }
     const int stream = mode == 2 ? 1 : 0;
     if (stream == 0) depend(0, 1);
-    push_gemm(level, phase, cfg, begin, count, flops, shared, stream);
+    push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, stream);
   }
-  // tile configuration is decided per launch: larger tiles only pay when they fill the GPU
-  void end_gemm(int level, int phase, bool top) {
-    int64_t n128 = 0;
-    for (const Pending &pd : pend)
-      if (is_big(D.probs[pd.prob])) n128 += ntiles(D.probs[pd.prob], D.big_cfg);
-    int64_t share = (top && D.world > 1) ? D.world : 1;
-    bool use128 = n128 >= (int64_t)D.min_tiles_128 * share;
+  void end_gemm(int level, int phase, bool small_ok) {
     // small fronts (bottom of the tree): one warp per 32x32 tile, operands straight from global memory
-    const bool small_ok = D.small_front && mode == 0 && !(top && D.world > 1);
-    std::vector<Pending> l128, l64, lsmall;
+    small_ok = small_ok && D.small_front && mode == 0;
+    std::vector<Pending> l64, lsmall;
     for (const Pending &pd : pend) {
       const GemmProblem &g = D.probs[pd.prob];
       int ksum = 0;
       for (int c = 0; c < g.contrib_count; c++) ksum += D.contribs[g.contrib_begin + c].K;
-      if (small_ok && g.M <= D.small_mn && g.N <= D.small_mn && ksum <= D.small_k) lsmall.push_back(pd);
-      else (use128 && is_big(g) ? l128 : l64).push_back(pd);
+      (small_ok && g.M <= D.small_mn && g.N <= D.small_mn && ksum <= D.small_k ? lsmall : l64).push_back(pd);
     }
-    emit(level, phase, D.big_cfg, l128, top);
-    emit(level, phase, 0, l64, top);
-    emit(level, phase, 3, lsmall, top);
+    emit(level, phase, 0, l64);
+    emit(level, phase, 3, lsmall);
   }
 };
 
@@ -214,22 +206,21 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if ((1 << depth) != world || rank < 0 || rank >= world) return err = "world size must be a power of two and 0 <= rank < world", -1;
   if (depth >= P.levels) return err = "more ranks than subtrees", -1;
   if (only_heap && (world != 1 || only_heap < 1 || only_heap > P.N)) return err = "a single-separator schedule needs a single-GPU handle and a valid separator", -1;
+  if (split_phases && world != 1) return err = "the piecewise fused tasks run on a single-GPU handle", -1;
   D.depth = depth;
-  if (const char *e = getenv("CHOL_BIG_CFG")) D.big_cfg = atoi(e);                    // tuning knob: 1 = 128x128, 2 = 128x64
-  if (const char *e = getenv("CHOL_MIN_TILES_128")) D.min_tiles_128 = atoi(e);        // tuning knob
-  if (const char *e = getenv("CHOL_SHARED_MIN_FLOPS")) D.shared_min_flops = atof(e);  // tests lower it to split small grids
   if (const char *e = getenv("CHOL_LOOKAHEAD")) D.lookahead = atoi(e) != 0;
   if (const char *e = getenv("CHOL_SMALL_FRONT")) D.small_front = atoi(e) != 0;
   if (const char *e = getenv("CHOL_SMALL_MN")) D.small_mn = atoi(e);
   if (const char *e = getenv("CHOL_SMALL_K")) D.small_k = atoi(e);
-  if (const char *e = getenv("CHOL_NBO")) D.nbo = std::max(64, atoi(e) / 64 * 64);  // tuning knob: block-column width
-  if (const char *e = getenv("CHOL_NBO_SMALL")) D.nbo_small = atoi(e) > 0 ? std::max(64, atoi(e) / 64 * 64) : 0;
-  if (const char *e = getenv("CHOL_NBO_SMALL_MAXN")) D.nbo_small_maxn = atoi(e);
+  if (const char *e = getenv("CHOL_NBO")) D.nbo = std::max(64, atoi(e) / 64 * 64);  // tuning knob: block-column width (single GPU)
+  if (const char *e = getenv("CHOL_ROW_BLOCK")) D.row_block = std::min(kRowBlock, std::max(64, atoi(e) / 64 * 64));
+  if (world > 1) D.nbo = D.row_block;  // the row blocks of the top panels are block columns
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
-  const int NB = D.nb, SLAB = D.slab;
+  const int NB = D.nb, SLAB = D.slab, NBO = D.nbo, RB = D.row_block;
+  const unsigned wmask = (1u << world) - 1u, me = 1u << rank;
   Builder B(P, S, D);
-  auto owner_of = [&](int h) -> int {  // -1: shared top separator
+  auto owner_of = [&](int h) -> int {  // -1: top separator (rows dealt to its group)
     int lv = P.level_of(h);
     return lv < depth ? -1 : (h >> (lv - depth)) - (1 << depth);
   };
@@ -250,7 +241,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   };
 
   // ---- assembly map (fill_block, mmat.rg:529-633, as a scatter).  With several ranks an entry is
-  // assembled by the owner of its column separator; top entries by rank 0 only (the copies are summed).
+  // assembled by the owner of its column separator; entries of the top panels by the owner of their row.
   if (!only_heap) {
     std::vector<int> iperm(P.n), rowheap(P.n);
     for (int p = 0; p < P.n; p++) iperm[P.perm[p]] = p;
@@ -267,18 +258,67 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
         int d = P.level_of(hc) - P.level_of(hr);
         if (d < 0 || (hc >> d) != hr) continue;
         int own = owner_of(hc);
-        if (world > 1 && !(own == rank || (own < 0 && rank == 0))) continue;
+        if (world > 1 && own >= 0 && own != rank) continue;
         int r = locate(hc, pi);
         if (r < 0) {
           bad[w] = 1;
           return;
         }
+        if (world > 1 && own < 0 && top_group(hc, P.level_of(hc), depth, RB).owner(r / RB) != rank) continue;
         D.a_off[e] = S.poff[hc] + r + (int64_t)(pj - P.start[hc]) * S.ld[hc];
       }
     });
     for (int b : bad)
       if (b) return err = "internal: nonzero outside the filled pattern", -1;
   }
+
+  // Schur destination (panel p, stored row crow, column ccol, M x N, tri) with contributors cs[0 .. cnt).
+  // `split`: the destination is a top panel updated from a top level -- every 256-row block of it is
+  // computed by its owner, this rank keeps its own blocks.  Operand tiles are fetched with 16-byte bulk
+  // copies, so a sub-problem starts on an even operand row; when the ownership boundary falls on an odd
+  // one the sub-problem starts one row early and that row is masked in the epilogue (tri bit 1).
+  auto add_dest = [&](const Pair *cs, size_t cnt, bool split) -> int {
+    const Pair &q = cs[0];
+    for (size_t c = 0; c < cnt; c++)
+      if (cs[c].M != q.M || cs[c].N != q.N || cs[c].tri != q.tri) return err = "internal: contributors of one destination cluster disagree on its shape", -1;
+    const int ldc = S.ld[q.p];
+    const int64_t c_off = S.poff[q.p] + q.crow + (int64_t)q.ccol * ldc;
+    auto sub = [&](int m0, int M, int n0, int N, int tri) {  // rows [m0, m0 + M) x cols [n0, n0 + N) of the destination
+      if (M <= 0 || N <= 0) return;
+      GemmProblem g;
+      g.c_off = c_off + m0 + (int64_t)n0 * ldc, g.ldc = ldc, g.M = M, g.N = N, g.tri = tri;
+      g.contrib_begin = (int)D.contribs.size(), g.contrib_count = (int)cnt;
+      double pf = 0;
+      for (size_t c = 0; c < cnt; c++) {
+        D.contribs.push_back(GemmContrib{cs[c].a_off + m0, cs[c].b_off + n0, cs[c].ld, cs[c].ld, cs[c].K, 0});
+        pf += Builder::gemm_flops(M, N, cs[c].K, tri);
+      }
+      D.probs.push_back(g);
+      Builder::Pending pd;
+      pd.prob = (int)D.probs.size() - 1, pd.flops = pf;
+      B.pend.push_back(pd);
+    };
+    if (!split) {
+      sub(0, q.M, 0, q.N, q.tri);
+      return 0;
+    }
+    if (q.tri && q.M != q.N) return err = "internal: a diagonal destination cluster is not square", -1;
+    const TopGroup grp = top_group(q.p, P.level_of(q.p), depth, RB);
+    for (int m0 = 0; m0 < q.M;) {
+      const int blk = (q.crow + m0) / RB;
+      const int m1 = std::min(q.M, (blk + 1) * RB - q.crow);
+      if (grp.owner(blk) == rank) {
+        const int e0 = m0 & ~1, skip = (m0 & 1) ? 2 : 0;
+        if (!q.tri) sub(e0, m1 - e0, 0, q.N, skip);
+        else {
+          sub(e0, m1 - e0, 0, e0, skip);        // columns left of the diagonal block of these rows
+          sub(e0, m1 - e0, e0, m1 - e0, 1 | skip);  // the diagonal block itself
+        }
+      }
+      m0 = m1;
+    }
+    return 0;
+  };
 
   std::vector<Pair> pairs;
   for (int lvl = L - 1; lvl >= 0; lvl--) {
@@ -291,86 +331,178 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
       h0 = ((1 << depth) + rank) << (lvl - depth);
       h1 = h0 + (1 << (lvl - depth));
     }
-    int maxn = 0;
-    for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
-    // block-column width of the level: narrower columns shorten the chain of small fronts (64^3, root 4 096:
-    // 28.3 ms at 128 against 29.5 at 256), wide ones keep the trailing updates of the big fronts efficient
-    // (128^3: 1 062 ms at 128 against 976 at 256).  The per-level choice is an experiment, off by default.
-    const int NBO = (D.nbo_small > 0 && maxn <= D.nbo_small_maxn) ? D.nbo_small : D.nbo;
-    const int nouter = (maxn + NBO - 1) / NBO;
     B.depend(1, 0);  // the chain of this level starts after the previous level's updates
 
-    // which == 0: pivot blocks (rows [0, n));  which == 1: off-diagonal rows [r0, R);  which == 2: both at
-    // once (rows [0, R)): the default, it halves the number of dependent small launches.  The split form
-    // serves the piecewise fused_dpotrf / fused_dtrsm entry points.
-    for (int which = (D.split_phases ? 0 : 2); which < (D.split_phases ? 2 : 3); which++) {
-      const int phase = which == 0 ? PH_POTRF : which == 1 ? PH_TRSM : (PH_POTRF | PH_TRSM);
-      for (int J = 0; J < nouter; J++) {
-        const int c0 = J * NBO;
-        for (int jj = 0; jj < NBO / NB; jj++) {
-          const int d0 = c0 + jj * NB;
-          if (d0 >= maxn) break;
-          if (which != 1) {
-            int64_t b = (int64_t)D.potrf.size();
-            for (int h = h0; h < h1; h++) {
-              int n = P.sz[h];
-              if (n <= d0) continue;
-              D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
+    if (!top) {
+      int maxn = 0;
+      for (int h = h0; h < h1; h++) maxn = std::max(maxn, P.sz[h]);
+      const int nouter = (maxn + NBO - 1) / NBO;
+      // which == 0: pivot blocks (rows [0, n));  which == 1: off-diagonal rows [r0, R);  which == 2: both at
+      // once (rows [0, R)): the default, it halves the number of dependent small launches.  The split form
+      // serves the piecewise fused_dpotrf / fused_dtrsm entry points.
+      for (int which = (D.split_phases ? 0 : 2); which < (D.split_phases ? 2 : 3); which++) {
+        const int phase = which == 0 ? PH_POTRF : which == 1 ? PH_TRSM : (PH_POTRF | PH_TRSM);
+        for (int J = 0; J < nouter; J++) {
+          const int c0 = J * NBO;
+          for (int jj = 0; jj < NBO / NB; jj++) {
+            const int d0 = c0 + jj * NB;
+            if (d0 >= maxn) break;
+            if (which != 1) {
+              int64_t b = (int64_t)D.potrf.size();
+              for (int h = h0; h < h1; h++) {
+                int n = P.sz[h];
+                if (n <= d0) continue;
+                D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
+              }
+              if ((int64_t)D.potrf.size() > b) B.push(Builder::mk(K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b), 1);
             }
-            if ((int64_t)D.potrf.size() > b) B.push(Builder::mk(K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b, 0, 0, 0), 1);
-          }
-          {
-            int64_t b = (int64_t)D.trsm_tiles.size();
+            {
+              int64_t b = (int64_t)D.trsm_tiles.size();
+              for (int h = h0; h < h1; h++) {
+                int n = P.sz[h], ld = S.ld[h];
+                if (n <= d0) continue;
+                int dw = std::min(NB, n - d0);
+                int rbeg = which == 1 ? (n + 1) / 2 * 2 : d0 + dw;
+                int rend = which == 0 ? n : S.rows[h];
+                if (rend <= rbeg) continue;
+                D.trsm.push_back(TrsmDesc{S.poff[h] + d0 + (int64_t)d0 * ld, S.poff[h] + rbeg + (int64_t)d0 * ld, ld, dw, rend - rbeg, 0});
+                int ns = (rend - rbeg + SLAB - 1) / SLAB;
+                for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
+              }
+              if ((int64_t)D.trsm_tiles.size() > b) B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
+            }
+            // right-looking update of the rest of this block column (K = NB)
+            B.begin_gemm(2);
             for (int h = h0; h < h1; h++) {
               int n = P.sz[h], ld = S.ld[h];
               if (n <= d0) continue;
-              int dw = std::min(NB, n - d0);
-              int rbeg = which == 1 ? (n + 1) / 2 * 2 : d0 + dw;
-              int rend = which == 0 ? n : S.rows[h];
-              if (rend <= rbeg) continue;
-              D.trsm.push_back(TrsmDesc{S.poff[h] + d0 + (int64_t)d0 * ld, S.poff[h] + rbeg + (int64_t)d0 * ld, ld, dw, rend - rbeg, 0});
-              int ns = (rend - rbeg + SLAB - 1) / SLAB;
-              for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
+              int dw = std::min(NB, n - d0), e0 = d0 + dw, cend = std::min(c0 + NBO, n);
+              if (e0 >= cend) continue;
+              int64_t base = S.poff[h];
+              if (which != 1)
+                B.add_problem(base + e0 + (int64_t)e0 * ld, ld, (which == 0 ? n : S.rows[h]) - e0, cend - e0, 1, base + e0 + (int64_t)d0 * ld,
+                              base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+              else {
+                int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
+                B.add_problem(base + r0 + (int64_t)e0 * ld, ld, m, cend - e0, 0, base + r0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+              }
             }
-            if ((int64_t)D.trsm_tiles.size() > b) B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b, 0, 0, 0), 1);
+            B.end_gemm(lvl, phase, false);
           }
-          // right-looking update of the rest of this block column (K = NB); replicated on a shared top panel
-          B.begin_gemm(2);
+          // right-looking update of everything to the right of block column J (K = NBO)
+          B.begin_gemm(1);
           for (int h = h0; h < h1; h++) {
             int n = P.sz[h], ld = S.ld[h];
-            if (n <= d0) continue;
-            int dw = std::min(NB, n - d0), e0 = d0 + dw, cend = std::min(c0 + NBO, n);
-            if (e0 >= cend) continue;
+            int c1 = c0 + NBO;
+            if (n <= c1) continue;
             int64_t base = S.poff[h];
+            const int next_tc = (std::min(NBO, n - c1) + 63) / 64;  // tile columns of the next block column
             if (which != 1)
-              B.add_problem(base + e0 + (int64_t)e0 * ld, ld, (which == 0 ? n : S.rows[h]) - e0, cend - e0, 1, base + e0 + (int64_t)d0 * ld,
-                            base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+              B.add_problem(base + c1 + (int64_t)c1 * ld, ld, (which == 0 ? n : S.rows[h]) - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld,
+                            base + c1 + (int64_t)c0 * ld, ld, ld, NBO, c1 / 64, next_tc);
             else {
               int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
-              B.add_problem(base + r0 + (int64_t)e0 * ld, ld, m, cend - e0, 0, base + r0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+              B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO,
+                            r0 / 64, next_tc);
             }
           }
-          B.end_gemm(lvl, phase, top);
+          B.end_gemm(lvl, phase, false);
         }
-        // right-looking update of everything to the right of block column J (K = NBO)
-        B.begin_gemm(1);
-        for (int h = h0; h < h1; h++) {
-          int n = P.sz[h], ld = S.ld[h];
-          int c1 = c0 + NBO;
-          if (n <= c1) continue;
-          int64_t base = S.poff[h];
-          const int next_tc = (std::min(NBO, n - c1) + 63) / 64;  // tile columns of the next block column
-          if (which != 1)
-            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, (which == 0 ? n : S.rows[h]) - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld,
-                          base + c1 + (int64_t)c0 * ld, ld, ld, NBO, c1 / 64, next_tc);
-          else {
-            int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
-            B.add_problem(base + r0 + (int64_t)c1 * ld, ld, m, n - c1, 0, base + r0 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, NBO,
-                          r0 / 64, next_tc);
-          }
-        }
-        B.end_gemm(lvl, phase, top);
       }
+    } else {
+      // ---- a top level: this rank works on the one separator above its subtree, with the rest of its group
+      const int p = ((1 << depth) + rank) >> (depth - lvl);
+      const TopGroup grp = top_group(p, lvl, depth, RB);
+      const unsigned gmask = grp.mask();
+      const int n = P.sz[p], R = S.rows[p], ld = S.ld[p], r0 = (n + 1) / 2 * 2;
+      const int64_t base = S.poff[p];
+      const int phase = PH_POTRF | PH_TRSM;
+      const int nblk = (R + RB - 1) / RB;
+      const int64_t lvl_seq = (int64_t)(depth - lvl) << 24;
+      B.own = &grp;
+      for (int J = 0; J * RB < n; J++) {
+        const int c0 = J * RB, w = std::min(RB, n - c0), c1 = c0 + w;
+        const int diag_owner = grp.owner(J);
+        const int below0 = c1 == n ? r0 : c1;  // first stored row below the diagonal block
+        // this rank's rows below the diagonal block, block by block
+        std::vector<std::pair<int, int>> mine;  // [begin, end)
+        for (int b = J; b < nblk; b++) {
+          if (grp.owner(b) != rank) continue;
+          const int rb = std::max(b * RB, below0), re = std::min((b + 1) * RB, R);
+          if (re > rb) mine.push_back({rb, re});
+        }
+        if (rank == diag_owner) {
+          // the diagonal block (w x w), tile by tile: POTRF, TRSM of the rows below inside the block, K = NB update
+          for (int d0 = c0; d0 < c1; d0 += NB) {
+            const int dw = std::min(NB, c1 - d0), e0 = d0 + dw;
+            D.potrf.push_back(PotrfDesc{base + d0 + (int64_t)d0 * ld, ld, dw, P.start[p] + d0, 0});
+            B.push(Builder::mk(K_POTRF, lvl, phase, (int64_t)D.potrf.size() - 1, 1), 1);
+            if (e0 >= c1) continue;
+            int64_t b = (int64_t)D.trsm_tiles.size();
+            D.trsm.push_back(TrsmDesc{base + d0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, dw, c1 - e0, 0});
+            for (int s = 0; s < (c1 - e0 + SLAB - 1) / SLAB; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)s, 0});
+            B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
+            B.begin_gemm(2);
+            B.add_problem(base + e0 + (int64_t)e0 * ld, ld, c1 - e0, c1 - e0, 1, base + e0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+            B.end_gemm(lvl, phase, false);
+          }
+          int64_t rb = (int64_t)D.rects.size();
+          D.rects.push_back(RectDesc{base + c0 + (int64_t)c0 * ld, ld, w, w, 0});
+          B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + J + 1, gmask & ~me, 1);
+        } else
+          B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
+        // own rows below: X <- X L_JJ^-T, 64 columns at a time
+        for (int d0 = c0; d0 < c1 && !mine.empty(); d0 += NB) {
+          const int dw = std::min(NB, c1 - d0), e0 = d0 + dw;
+          int64_t b = (int64_t)D.trsm_tiles.size();
+          for (auto &rg : mine) {
+            D.trsm.push_back(TrsmDesc{base + d0 + (int64_t)d0 * ld, base + rg.first + (int64_t)d0 * ld, ld, dw, rg.second - rg.first, 0});
+            for (int s = 0; s < (rg.second - rg.first + SLAB - 1) / SLAB; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)s, 0});
+          }
+          B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
+          if (e0 >= c1) continue;
+          B.begin_gemm(2);
+          for (auto &rg : mine)
+            B.add_problem(base + rg.first + (int64_t)e0 * ld, ld, rg.second - rg.first, c1 - e0, 0, base + rg.first + (int64_t)d0 * ld,
+                          base + e0 + (int64_t)d0 * ld, ld, ld, dw);
+          B.end_gemm(lvl, phase, false);
+        }
+        // the group needs the pivot-block rows of this block column for its trailing updates: push them now ...
+        {
+          int64_t rb = (int64_t)D.rects.size();
+          for (auto &rg : mine)
+            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri});
+          B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 1);
+        }
+        // ... and, in the background, everything else to everybody (needed from the end of the level on)
+        {
+          B.depend(2, 1);
+          int64_t rb = (int64_t)D.rects.size();
+          for (auto &rg : mine)
+            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri});
+          B.push_rects(lvl, phase, rb, wmask & ~gmask, 0, 0, 0, 2);
+          rb = (int64_t)D.rects.size();
+          for (auto &rg : mine)
+            if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri});
+          B.push_rects(lvl, phase, rb, wmask & ~me, 0, 0, 0, 2);
+        }
+        // trailing update of this rank's rows (K = w); its B operand is the group's pushed rows
+        B.depend(0, 1);
+        B.sync(lvl, phase, SLOT_GROUP, lvl_seq + J + 1, 0, gmask & ~me, 0);
+        B.begin_gemm(1);
+        if (n > c1) {
+          const int next_tc = (std::min(RB, n - c1) + 63) / 64;
+          B.add_problem(base + c1 + (int64_t)c1 * ld, ld, R - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, w,
+                        c1 / 64, next_tc);
+        }
+        B.end_gemm(lvl, phase, false);
+      }
+      B.own = nullptr;
+      // every rank holds the complete panels of the level once all pushes have landed
+      B.depend(0, 1);
+      B.depend(0, 2);
+      B.sync(lvl, PH_UPDATE, SLOT_WORLD, lvl_seq + 1, wmask & ~me, wmask & ~me, 0);
+      h0 = 1 << lvl, h1 = 1 << (lvl + 1);  // the Schur updates below take contributions from every panel of the level
     }
 
     // ---- (c) Schur updates of the level, grouped by destination cluster
@@ -404,45 +536,34 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     for (size_t i = 0; i < pairs.size();) {
       size_t j = i;
       while (j < pairs.size() && pairs[j].p == pairs[i].p && pairs[j].ccol == pairs[i].ccol && pairs[j].crow == pairs[i].crow) j++;
-      const Pair &q = pairs[i];
-      GemmProblem g;
-      g.c_off = S.poff[q.p] + q.crow + (int64_t)q.ccol * S.ld[q.p];
-      g.ldc = S.ld[q.p], g.M = q.M, g.N = q.N, g.tri = q.tri;
-      g.contrib_begin = (int)D.contribs.size(), g.contrib_count = (int)(j - i);
-      double pf = 0;
-      for (size_t c = i; c < j; c++) {
-        if (pairs[c].M != q.M || pairs[c].N != q.N || pairs[c].tri != q.tri) return err = "internal: contributors of one destination cluster disagree on its shape", -1;
-        D.contribs.push_back(GemmContrib{pairs[c].a_off, pairs[c].b_off, pairs[c].ld, pairs[c].ld, pairs[c].K, 0});
-        pf += 2.0 * pairs[c].K * ((double)q.M * q.N - (q.tri ? 0.5 * q.N * (q.N - 1.0) : 0.0));
-      }
-      D.probs.push_back(g);
-      Builder::Pending pd;
-      pd.prob = (int)D.probs.size() - 1, pd.flops = pf;
-      B.pend.push_back(pd);
+      if (add_dest(&pairs[i], j - i, top)) return -1;
       i = j;
     }
-    B.end_gemm(lvl, PH_UPDATE, top);
+    B.end_gemm(lvl, PH_UPDATE, !top);
 
-    // the subtrees are done: sum every rank's copy of the top panels before the top is factored
-    // One reduction per top panel: only the ranks under that separator (and rank 0, which assembled A's
-    // entries) hold contributions, and the strictly upper part of the pivot block is never touched.
+    // the subtrees are done: every rank sums, for the rows it owns in each top panel above its subtree, the
+    // partial sums of that panel's group (the strictly upper part of a pivot block is never touched)
     if (world > 1 && lvl == depth) {
       B.depend(0, 1);
-      B.push(Builder::mk(K_BARRIER, lvl, PH_UPDATE, 0, 0, 0, 0, 0), 0);
-      for (int h = 1; h < (1 << depth); h++) {
-        const int lv = P.level_of(h);
-        unsigned mask = 1u;  // rank 0
-        for (int r = 0; r < world; r++)
-          if ((((1 << depth) + r) >> (depth - lv)) == h) mask |= 1u << r;
-        // begin = panel offset, count = panel doubles, cfg = contributor mask, shared = heap index of the panel
-        B.push(Builder::mk(K_ALLREDUCE, lvl, PH_UPDATE, S.poff[h], S.poff[h + 1] - S.poff[h], 0, (int)mask, h), 0);
+      B.sync(lvl, PH_UPDATE, SLOT_WORLD, 1, wmask & ~me, wmask & ~me, 0);
+      for (int lv = depth - 1; lv >= 0; lv--) {
+        const int p = ((1 << depth) + rank) >> (depth - lv);
+        const TopGroup grp = top_group(p, lv, depth, RB);
+        const int R = S.rows[p];
+        int64_t rb = (int64_t)D.rects.size();
+        for (int b = 0; b * RB < R; b++)
+          if (grp.owner(b) == rank) D.rects.push_back(RectDesc{S.poff[p] + b * RB, S.ld[p], std::min(RB, R - b * RB), P.sz[p], b * RB});
+        Launch l = Builder::mk(K_REDUCE, lvl, PH_UPDATE, rb, (int64_t)D.rects.size() - rb);
+        l.mask = grp.mask();
+        if (l.count > 0) B.push(l, 0);
       }
-      B.push(Builder::mk(K_BARRIER, lvl, PH_UPDATE, 0, 0, 0, 0, 0), 0);
+      B.sync(lvl, PH_UPDATE, SLOT_WORLD, 2, wmask & ~me, wmask & ~me, 0);
     }
   }
   // the step ends on stream 0
   B.depend(0, 1);
-  if (B.pendw[0] >= 0) B.push(Builder::mk(K_NOP, 0, 0, 0, 0, 0, 0, 0), 0);
+  B.depend(0, 2);
+  if (B.pendw[0] >= 0) B.push(Builder::mk(K_NOP, 0, 0), 0);
   if (D.contribs.size() > 0x7fffffffULL || D.probs.size() > 0x7fffffffULL) return err = "schedule too large", -1;
   return 0;
 }

@@ -1,11 +1,14 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed only for the bootstrap.
+"""Multi-GPU plumbing for the one-process-per-GPU form (torchrun); torch.distributed only for the bootstrap.
+(Inside one process, Cholesky(devices=[...]) drives the same partition through a group handle.)
 
-Rank r owns the subtree under heap index world + r; the log2(world) top levels are shared
-(SURVEY.md 8e).  The data path never goes through torch or NCCL: after the ranks have exchanged the
-CUDA-IPC handles of their factor buffers and flag words (one all_gather of 128 bytes per rank), the
-engine's own kernels sum the top-panel copies and broadcast the tiles of the shared launches through
-NVLink peer memory, and synchronise with a flag barrier in peer memory (csrc/kernels.cuh).
+Rank r owns the subtree under heap index world + r; the rows of the log2(world) top levels' panels are dealt
+to the ranks under each separator in blocks of 256 (csrc/schedule.cc).  The data path never goes
+through torch or NCCL: after the ranks have exchanged the CUDA-IPC handles of their factor buffers and flag words
+(one all_gather of 128 bytes per rank), the engine's own kernels pull the partial sums of the rows a rank owns,
+push factored rows into the peers' copies and meet in flag words, all through NVLink peer memory (csrc/kernels.cuh).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -15,6 +18,8 @@ from .engine import Cholesky
 def make_partitioned(grid=None, files=None, keep_records=False):
     """build this rank's engine: generate/load, set the partition, analyse"""
     rank, world = dist.get_rank(), dist.get_world_size()
+    # the ranks of one node share its host cores for the symbolic analysis
+    os.environ.setdefault("CHOL_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // world))))
     dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
     ch = Cholesky(dev)
     if grid is not None:
@@ -68,3 +73,10 @@ def solve(ch, b):
     doubles) and the assembly of the owned pieces of x at the end."""
     top = _sum_over_ranks(ch.solve_forward(b))
     return _sum_over_ranks(ch.solve_backward(top))
+
+
+def residual(ch, k=4, seed=1):
+    """randomized ||(A - L L^T) W||_F / ||A W||_F of a partitioned factor: every rank evaluates its panels' share of
+    L (L^T W) on its GPU, the (n, 4) shares are summed over the ranks, the comparison with A W runs on the host"""
+    z = _sum_over_ranks(ch.residual_partial(k=k, seed=seed))
+    return ch.residual_finish(z, k=k, seed=seed)

@@ -17,18 +17,41 @@ class CholeskyError(RuntimeError):
 
 
 class Cholesky:
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """one GPU (`device`), or a group of 2, 4 or 8 GPUs driven from this process (`devices`: CUDA ordinals;
+        repeating one makes several ranks share it)"""
         self.L = _lib.load()
         self.h = C.c_void_p()
-        dev = (C.c_int * 1)(device)
-        if self.L.chol_create(dev, 1, C.byref(self.h)) != 0:
-            raise CholeskyError("chol_create failed")
+        devs = list(devices) if devices is not None else [device]
+        arr = (C.c_int * len(devs))(*devs)
+        if self.L.chol_create(arr, len(devs), C.byref(self.h)) != 0:
+            raise CholeskyError(f"chol_create failed (devices {devs}: 1, 2, 4 or 8 GPUs)")
+        self._owned = True
+
+    @classmethod
+    def _borrowed(cls, handle, parent):
+        self = cls.__new__(cls)
+        self.L, self.h, self._owned, self._parent = parent.L, C.c_void_p(handle), False, parent
+        for k in ("n", "nz", "levels", "num_separators"):
+            if hasattr(parent, k):
+                setattr(self, k, getattr(parent, k))
+        return self
+
+    def num_ranks(self):
+        return int(self.L.chol_num_ranks(self.h))
+
+    def rank_handle(self, r):
+        """rank r of a group handle, for the per-rank inspection calls (partition_stats, launches, ...)"""
+        h = self.L.chol_rank_handle(self.h, r)
+        if not h:
+            raise CholeskyError(f"no rank {r}")
+        return Cholesky._borrowed(h, self)
 
     # ---- lifecycle
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and getattr(self, "_owned", False):
             self.L.chol_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -177,8 +200,14 @@ class Cholesky:
     def partition_stats(self):
         out = np.zeros(6, dtype=np.float64)
         self._ck(self.L.chol_partition_stats(self.h, _p(out)))
-        return dict(assembled=int(out[0]), gemm_flops=float(out[1]), shared_launches=int(out[2]),
+        return dict(assembled=int(out[0]), gemm_flops=float(out[1]), push_launches=int(out[2]),
                     top_doubles=int(out[3]), potrf_tiles=int(out[4]), trsm_slabs=int(out[5]))
+
+    def top_copies_diff(self):
+        """largest |difference| between the ranks' copies of the factored top panels (0 = bit-identical)"""
+        d = C.c_double()
+        self._ck(self.L.chol_top_copies_diff(self.h, C.byref(d)))
+        return d.value
 
     def launch_times(self):
         """per-launch device ms of the last kernel_times() pass (launch-list order)"""
@@ -195,9 +224,9 @@ class Cholesky:
         for i in range(int(self.L.chol_num_launches(self.h))):
             self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
                                    C.byref(ctas), C.byref(flops), C.byref(cfg))
-            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_barrier", "allreduce_top", "nop")
+            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_sync", "reduce_rects", "nop", "push_rects", "panel")
             out.append(dict(kind=names[kind.value], level=level.value, phase=phase.value, ctas=ctas.value,
-                            flops=flops.value, cfg=cfg.value & 15, shared=cfg.value >> 4))
+                            flops=flops.value, cfg=cfg.value & 15, stream=cfg.value >> 4))
         return out
 
     # ---- results (mmat.rg:1360-1362)
@@ -236,9 +265,22 @@ class Cholesky:
         """level loop one fused task group at a time on the GPU, one snapshot file per reference task"""
         self._ck(self.L.chol_factor_debug(self.h, directory.encode(), 1 if full_precision else 0, 1 if with_txt else 0))
 
-    def residual(self, k=16, seed=1):
+    def residual(self, k=4, seed=1):
+        """randomized ||(A - L L^T) W|| / ||A W||, k <= 4 probe columns, evaluated on the GPU (single-GPU or group handle)"""
         r = C.c_double()
-        self._ck(self.L.chol_residual(self.h, k, C.c_uint64(seed), C.byref(r)))
+        self._ck(self.L.chol_residual(self.h, min(k, 4), C.c_uint64(seed), C.byref(r)))
+        return r.value
+
+    def residual_partial(self, k=4, seed=1):
+        """this rank's share of Z = L (L^T W): (n, 4) array, permuted rows (see distributed.residual)"""
+        z = np.zeros((self.n, 4), dtype=np.float64)
+        self._ck(self.L.chol_residual_partial(self.h, k, C.c_uint64(seed), _p(z)))
+        return z
+
+    def residual_finish(self, z_sum, k=4, seed=1):
+        z = np.ascontiguousarray(z_sum, dtype=np.float64)
+        r = C.c_double()
+        self._ck(self.L.chol_residual_finish(self.h, k, C.c_uint64(seed), _p(z), C.byref(r)))
         return r.value
 
     def matvec(self, x):

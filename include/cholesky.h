@@ -9,7 +9,9 @@
  * leaf tasks, and the loaders/writers keep the reference's file formats (mmio.c, mnd.c,
  * mmat.rg:102-147).  Plain pointers and sizes only; int return 0 = ok, <0 = error
  * (chol_last_error gives the text).  Host pointers are borrowed; device memory is owned by the
- * handle.  One host thread drives a handle; one handle drives one GPU.
+ * handle.  One host thread drives a handle.  A handle drives one GPU, or (chol_create with ngpu = 2, 4
+ * or 8) a group of GPUs of one node from one process: the same calls then run subtree-partitioned over
+ * the devices listed, which exchange data through NVLink peer memory.
  */
 #ifndef __CHOLESKY_H__
 #define __CHOLESKY_H__
@@ -37,8 +39,14 @@ typedef struct {
   int info;                                          /* 0, or 1-based permuted column of a non-positive pivot */
 } chol_stats_t;
 
-/* ---- lifecycle.  replaces: regentlib.start(main, register_mappers) (mmat.rg:1498) */
+/* ---- lifecycle.  replaces: regentlib.start(main, register_mappers) (mmat.rg:1498) and the processor
+ * selection of its command line (-ll:gpu / -ll:cpu).  devices[0 .. ngpu): CUDA device ordinals, ngpu = 1, 2, 4
+ * or 8 (anything else is refused); a device may be listed more than once (several ranks then share it: a
+ * way to exercise the partitioned path on one GPU). */
 int chol_create(const int *devices, int ngpu, chol_t **out);
+int chol_num_ranks(chol_t *);                /* 1, or ngpu of a group handle */
+chol_t *chol_rank_handle(chol_t *, int r);   /* borrowed handle of rank r of a group, for the per-rank inspection calls
+                                                (chol_partition_stats, chol_get_launch, chol_launch_times, chol_solve_stats) */
 void chol_destroy(chol_t *);
 const char *chol_last_error(chol_t *);
 void register_mappers(void); /* kept so that anything linking the old symbol still resolves; no-op */
@@ -99,8 +107,10 @@ int chol_fused_update(chol_t *, int lvl);
  * factor, and read back diag(L) in permuted order.  values may be NULL (reuse the loaded ones). */
 int chol_factor_host(chol_t *, const double *values, int64_t nz, double *diag_out, chol_stats_t *stats);
 int chol_synchronize(chol_t *);
-/* the compiled launch list: kind 0 potrf_tile / 1 trsm_tile / 2 gemm_grouped, tree level, phase
- * (1 fused_dpotrf, 2 fused_dtrsm, 4 fused_dsyrk+dgemm), CTAs, executed flops, tile configuration */
+/* the compiled launch list: kind 0 potrf_tile / 1 trsm_tile / 2 gemm_grouped / 3 peer_sync / 4 reduce_rects /
+ * 5 (no kernel: a cross-stream dependency) / 6 push_rects, tree level, phase (1 fused_dpotrf, 2 fused_dtrsm,
+ * 4 fused_dsyrk+dgemm), CTAs or rectangles, executed flops, cfg = GEMM kernel (0: 64x64 tiles, 3: warp tiles)
+ * + 16 * stream (0 update, 1 chain, 2 background pushes) */
 int64_t chol_num_launches(chol_t *);
 int chol_get_launch(chol_t *, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg);
 /* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
@@ -108,20 +118,29 @@ int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_
 /* per-launch device time (ms) of that instrumented pass, in launch-list order; returns the count */
 int64_t chol_launch_times(chol_t *, float *ms, int64_t cap);
 
-/* ---- multi-GPU (one process and one handle per GPU; world = 1, 2, 4 or 8).  Rank r owns the subtree
- * under heap index world + r; the top log2(world) levels are shared.  Call chol_set_partition before
- * chol_analyze, then exchange the 128-byte IPC blobs of all ranks (any host-side all-gather) and hand
- * the concatenation to chol_ipc_import; the factorization then exchanges data through NVLink peer
- * memory from inside its own kernels.  Result accessors report the panels the rank owns (rank 0 also
- * the shared top). */
+/* ---- multi-GPU, one process and one handle per GPU (world = 1, 2, 4 or 8; the form torchrun / MPI
+ * launchers need -- inside one process use a group handle instead).  Rank r owns the subtree under heap
+ * index world + r; the rows of the top log2(world) levels' panels are dealt to the ranks below each
+ * separator in blocks of 256 and every rank ends up holding the complete factored top panels.  Call
+ * chol_set_partition before chol_analyze, then exchange the 128-byte IPC blobs of all ranks (any
+ * host-side all-gather) and hand the concatenation to chol_ipc_import; the factorization then exchanges
+ * data through NVLink peer memory from inside its own kernels.  Every rank must make the same sequence of
+ * chol_factor / chol_factor_host / chol_kernel_times calls.  Result accessors report the panels the rank
+ * owns (rank 0 also the top panels). */
 int chol_set_partition(chol_t *, int rank, int world);
 int chol_ipc_export(chol_t *, void *handles128);
 int chol_ipc_import(chol_t *, const void *all_handles, int world);
 /* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
- * [2] tile-split (shared) launches, [3] doubles of the shared top region, [4] potrf tiles, [5] trsm slabs */
+ * [2] peer-store launches (rows pushed to other ranks), [3] doubles of the top panels, [4] potrf tiles, [5] trsm slabs */
 int chol_partition_stats(chol_t *, double *out6);
 int chol_rank(chol_t *);
 int chol_world(chol_t *);
+/* verification: largest |difference| between the ranks' copies of the factored top panels, compared on the GPUs
+ * through peer memory (each rank against the next one; a group handle reports the largest); 0 = bit-identical */
+int chol_top_copies_diff(chol_t *, double *maxdiff);
+/* verification: largest |difference| between the ranks' copies of the factored top panels, compared on the GPUs
+ * through peer memory (each rank against the next one; a group handle reports the largest); 0 = bit-identical */
+int chol_top_copies_diff(chol_t *, double *maxdiff);
 
 /* ---- results.  replaces: write_matrix (mmat.rg:102-147) */
 int64_t chol_factor_nnz(chol_t *);                                           /* entries != 0 */
@@ -134,8 +153,14 @@ int chol_write_factor(chol_t *, const char *path, int full_precision);     /* "%
  * -3 cannot write, -4 truncated or corrupt, -5 entry count differs from the header. */
 int chol_write_factor_binary(chol_t *, const char *path);
 int chol_factor_binary_to_mtx(const char *bin_path, const char *mtx_path, int full_precision);
-/* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F, W = k Rademacher columns (seeded) */
+/* relative residual estimate ||(A - L L^T) W||_F / ||A W||_F, W = k <= 4 Rademacher columns (seeded).  Z = L (L^T W)
+ * is evaluated on the GPU from the factor where it sits (two coalesced passes over it, nothing but n x 4 doubles
+ * comes back), A W on the host from the loaded entries.  Partitioned handles: every rank calls
+ * chol_residual_partial (its panels' share of Z, n x 4 doubles, permuted row order), the caller sums the shares
+ * over the ranks and hands the sum to chol_residual_finish on any rank. */
 int chol_residual(chol_t *, int k, uint64_t seed, double *rel);
+int chol_residual_partial(chol_t *, int k, uint64_t seed, double *z_out_nx4);
+int chol_residual_finish(chol_t *, int k, uint64_t seed, const double *z_sum_nx4, double *rel);
 
 /* ---- debug trace (next row f-3).  replaces: the `-d <dir>` path of mmat.rg (1086-1090): the log lines
  * printed with debug = true (mmat.rg:331, 352, 396, 432, 1010; blas.rg:308, 340, 405, 422, 490) and the
@@ -148,7 +173,7 @@ int chol_write_debug_log(chol_t *, const char *log_path);
 int chol_factor_debug(chol_t *, const char *dir, int full_precision, int with_txt);
 
 /* ---- solve (next row f-1).  replaces: mmat.rg:1364-1495, blas.rg:217-290, mnd.c:201-229 */
-int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out; single-GPU handle */
+int chol_solve(chol_t *, const double *b, double *x); /* original dof order in and out; single-GPU or group handle */
 /* the same sweeps on a partitioned handle (after chol_set_partition / chol_ipc_import / chol_factor): every
  * rank calls chol_solve_forward with the whole b and gets its contribution to the shared top rows
  * (chol_solve_top_size doubles); the caller sums those over the ranks (any host-side all-reduce) and hands

@@ -5,7 +5,7 @@ residual <= 1e-12, pattern bit-exact."""
 import numpy as np
 import pytest
 
-from conftest import CASES, entrywise_ok
+from conftest import CASES, compare_coo, entrywise_ok
 from cholesky_b200 import Cholesky, read_vector
 from oracle import oracle as orc
 
@@ -134,20 +134,70 @@ def test_not_positive_definite_is_reported(golden, tmp_path):
         ch.factor()
 
 
-def test_config2_512x512_properties():
-    """BASELINE config 2 at full size through size-independent properties"""
-    ch = Cholesky().generate(512, 512, 1, 5, 0).analyze()
+def _entrywise_vs_oracle(grid, tmp_path, threads=8):
+    """factor a generated grid on the GPU and with the CPU oracle; compare every stored entry and the solve"""
+    m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
+    ch = Cholesky().generate(*grid)
+    ch.write_inputs(m, o, c)
+    ch.analyze()
     st = ch.factor()
     assert st.info == 0
     assert ch.residual(k=4) <= 1e-12
+    ref = orc.Oracle(m, o, c)
+    ref.factor(threads=threads)
+    same, worst = compare_coo(ch.n, ch.factor_coo(), ref.factor_coo())
+    assert same, "structural nonzeros differ from the oracle's"
+    assert worst <= 1e-10, worst
+    b = np.random.default_rng(0).integers(1, 11, size=ch.n).astype(np.float64)
+    x = ch.solve(b)
+    assert np.linalg.norm(b - ch.matvec(x)) <= 1e-12 * np.linalg.norm(b)
+    return ch
 
 
-def test_config3_64cubed_properties():
-    """BASELINE config 3 at full size: residual estimator + solve round trip"""
-    ch = Cholesky().generate(64, 64, 64, 7, 0).analyze()
-    st = ch.factor()
-    assert st.info == 0
-    assert ch.residual(k=2) <= 1e-12
+def test_config2_512x512_entrywise(tmp_path):
+    """BASELINE config 2 at full size (262 144 unknowns, 1.9e7 factor entries): every entry against the oracle"""
+    _entrywise_vs_oracle((512, 512, 1, 5, 0), tmp_path)
+
+
+def test_config3_64cubed_entrywise(tmp_path):
+    """BASELINE config 3 at full size (262 144 unknowns, 1.6e8 factor entries): every entry against the oracle"""
+    _entrywise_vs_oracle((64, 64, 64, 7, 0), tmp_path)
+
+
+def test_config5_stencil_entrywise(tmp_path):
+    """the 27-point stencil of BASELINE config 5 on a 40^3 grid (larger fronts per unknown): every entry against the oracle"""
+    _entrywise_vs_oracle((40, 40, 40, 27, 0), tmp_path)
+
+
+def test_solve_and_results_are_refused_after_a_failed_factorization(golden, tmp_path):
+    from cholesky_b200 import CholeskyError
+    g = golden["lapl_25x25"]
+    bad = tmp_path / "neg.mtx"
+    bad.write_text(open(g.mtx).read().replace("1 1 4.0", "1 1 -4.0", 1))
+    ch = Cholesky().load(str(bad), g.ord, g.clust).analyze()
+    with pytest.raises(CholeskyError, match="not positive definite"):
+        ch.factor()
+    with pytest.raises(CholeskyError, match="factor first"):
+        ch.solve(np.ones(ch.n))
+    with pytest.raises(CholeskyError, match="factor first"):
+        ch.residual()
+
+
+def test_reload_invalidates_device_state(golden):
+    """a handle that is reloaded must not serve results of (or index into) the previous problem"""
+    from cholesky_b200 import CholeskyError
+    g, g2 = golden["lapl_3375x3375"], golden["lapl_400x400"]
+    ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()
+    ch.factor()
+    ch.load(g2.mtx, g2.ord, g2.clust)
+    with pytest.raises(CholeskyError):
+        ch.solve(np.ones(g2.n))
+    with pytest.raises(CholeskyError):
+        ch.factor_nnz()
+    ch.analyze()
+    ch.factor()
+    ok, worst = entrywise_ok(ch.factor_dense(), g2.L_dense())
+    assert ok, worst
 
 
 @pytest.mark.parametrize("case", ["lapl_400x400", "lapl_3375x3375"])
