@@ -68,6 +68,8 @@ struct chol {
   bool h_fac_valid = false;
   std::vector<cudaEvent_t> evs;  // cross-stream events of the launch list
   cudaEvent_t ev_fork = nullptr, ev_join[kStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};  // timing events of a step
+  std::vector<cudaEvent_t> kev;                      // two per launch, for the instrumented pass
   double k_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double k_gemm_flops = 0;
   std::vector<float> launch_ms;  // per launch, from the last instrumented pass
@@ -186,6 +188,12 @@ static void free_device(chol_t *c) {
   c->evs.clear();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   c->ev_fork = nullptr;
+  for (cudaEvent_t &e : c->tev) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  }
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  c->kev.clear();
   for (int i = 0; i < kStreams; i++) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -404,6 +412,21 @@ static int rank_device(chol_t *c) {  // one rank: streams, buffers, descriptor a
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
   CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
   CK(cudaFuncSetAttribute(gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMain::kSmemBytes));
+  {  // load every kernel now: with lazy module loading the first launch of a function synchronises the context, which
+     // must not happen while another rank that shares this device is already spinning on a flag
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, potrf_tile));
+    CK(cudaFuncGetAttributes(&fa, trsm_tile));
+    CK(cudaFuncGetAttributes(&fa, gemm_small_warp));
+    CK(cudaFuncGetAttributes(&fa, gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>));
+    CK(cudaFuncGetAttributes(&fa, assemble_kernel));
+    CK(cudaFuncGetAttributes(&fa, gather_diag_kernel));
+    CK(cudaFuncGetAttributes(&fa, peer_sync));
+    CK(cudaFuncGetAttributes(&fa, push_rects));
+    CK(cudaFuncGetAttributes(&fa, reduce_rects));
+    CK(cudaFuncGetAttributes(&fa, compare_rects));
+  }
+  for (cudaEvent_t &e : c->tev) CK(cudaEventCreate(&e));
   CK(cudaMalloc((void **)&c->d_flags, kFlagSlots * kMaxPeers * sizeof(unsigned long long)));
   CK(cudaMemset(c->d_flags, 0, kFlagSlots * kMaxPeers * sizeof(unsigned long long)));
   CK(cudaMalloc((void **)&c->d_counters, kStreams * sizeof(unsigned)));
@@ -512,13 +535,9 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   std::vector<cudaEvent_t> ev;
   std::vector<int> kinds;
   std::vector<double> fl;
-  // cross-stream events of the launch list (look-ahead); the other streams start after whatever is
-  // already queued on the main stream (assembly)
-  while ((int)c->evs.size() < c->D.num_events) {
-    cudaEvent_t e;
-    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->evs.push_back(e);
-  }
+  if ((int)c->evs.size() < c->D.num_events || (per_kernel_timing && c->kev.size() < 2 * c->D.launches.size()))
+    return fail(c, "internal: prepare_rank has to run before the level loop");
+  size_t kev_next = 0;
   const bool whole = lvl_from >= c->P.levels - 1 && lvl_to <= 0 && phase_mask == 7;
   if (c->world > 1 && !whole) return fail(c, "partial runs of the level loop need a single-GPU handle");
   if (whole) c->run_id++;
@@ -543,8 +562,7 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
     c->cur = per_kernel_timing ? c->stream : c->streams[l.stream];
     if (l.wait_ev >= 0 && !per_kernel_timing) cudaStreamWaitEvent(c->cur, c->evs[l.wait_ev], 0);
     if (per_kernel_timing) {
-      cudaEvent_t a, b;
-      cudaEventCreate(&a), cudaEventCreate(&b);
+      cudaEvent_t a = c->kev[kev_next++], b = c->kev[kev_next++];
       cudaEventRecord(a, c->cur);
       run_launch(c, l);
       cudaEventRecord(b, c->cur);
@@ -586,7 +604,6 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
       c->k_ms[kinds[i]] += ms;
       c->launch_ms[i] = ms;
       if (kinds[i] == K_GEMM) c->k_gemm_flops += fl[i];
-      cudaEventDestroy(ev[2 * i]), cudaEventDestroy(ev[2 * i + 1]);
     }
   }
   return 0;
@@ -622,13 +639,34 @@ static int info_error(chol_t *c, int info) {
   return fail(c, "matrix is not positive definite: pivot at permuted column " + std::to_string(info));
 }
 
+// Everything a step needs that allocates or may synchronise the device (schedule upload, events, pinned staging
+// buffer) is done here, for ALL ranks of a group, before any rank issues a launch: once a rank's kernels spin on
+// flag words, a device-wide synchronisation by another rank that shares the GPU could never return.
+static int prepare_rank(chol_t *c, bool pinned, bool instrumented) {
+  if (ensure_schedule(c, false)) return -1;
+  while ((int)c->evs.size() < c->D.num_events) {  // cross-stream events of the launch list (look-ahead)
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->evs.push_back(e);
+  }
+  while (instrumented && c->kev.size() < 2 * c->D.launches.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    c->kev.push_back(e);
+  }
+  const size_t need = std::max((size_t)c->P.nz, (size_t)c->P.n) * sizeof(double);
+  if (pinned && c->h_pinned_bytes < need) {
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    CK(cudaMallocHost((void **)&c->h_pinned, need));
+    c->h_pinned_bytes = need;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // one rank: `warmup + iterations` x (assemble; level loop), device time of every timed level loop
 static int factor_rank(chol_t *c, int iterations, int warmup, std::vector<double> &secs, double &asm_s, int &info) {
-  if (ensure_schedule(c, false)) return -1;
-  cudaEvent_t e0, e1, e2;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  CK(cudaEventCreate(&e2));
+  cudaEvent_t e0 = c->tev[0], e1 = c->tev[1], e2 = c->tev[2];
   for (int it = 0; it < warmup + iterations; it++) {
     CK(cudaEventRecord(e0, c->stream));
     if (do_assemble(c)) return -1;
@@ -641,7 +679,6 @@ static int factor_rank(chol_t *c, int iterations, int warmup, std::vector<double
     CK(cudaEventElapsedTime(&mf, e1, e2));
     if (it >= warmup) secs.push_back(mf * 1e-3), asm_s = ma * 1e-3;
   }
-  cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2);
   return fetch_info(c, &info);
 }
 
@@ -653,6 +690,7 @@ int chol_factor(chol_t *c, int iterations, int warmup, chol_stats_t *st) {
   std::vector<std::vector<double>> secs(nr);
   std::vector<double> asm_s(nr, 0.0);
   std::vector<int> info(nr, 0);
+  if (for_ranks(c, [](chol_t *r) { return prepare_rank(r, false, false); })) return -1;
   if (for_ranks(c, [&](chol_t *r) { return factor_rank(r, iterations, warmup, secs[r->parent ? r->rank : 0], asm_s[r->parent ? r->rank : 0], info[r->parent ? r->rank : 0]); }))
     return -1;
   // a step of a group takes as long as its slowest rank
@@ -691,6 +729,11 @@ static int piecewise(chol_t *c, int lvl, int phase) {
   if (!c->assembled) return fail(c, "assemble first");
   if (lvl < 0 || lvl >= c->P.levels) return fail(c, "bad level");
   if (ensure_schedule(c, phase != PH_UPDATE || c->D.split_phases)) return -1;
+  while ((int)c->evs.size() < c->D.num_events) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->evs.push_back(e);
+  }
   c->h_fac_valid = false;
   if (run_levels(c, lvl, lvl, phase, false)) return -1;
   CK(cudaStreamSynchronize(c->stream));
@@ -703,16 +746,7 @@ int chol_fused_update(chol_t *c, int lvl) { return piecewise(c, lvl, PH_UPDATE);
 
 // one rank of chol_factor_host: H2D of the values, assemble, level loop, D2H of diag(L)
 static int factor_host_rank(chol_t *c, const double *values, double &secs, int &info) {
-  if (ensure_schedule(c, false)) return -1;
-  size_t need = std::max((size_t)c->P.nz, (size_t)c->P.n) * sizeof(double);
-  if (c->h_pinned_bytes < need) {
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    CK(cudaMallocHost((void **)&c->h_pinned, need));
-    c->h_pinned_bytes = need;
-  }
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  cudaEvent_t e0 = c->tev[0], e1 = c->tev[1];
   CK(cudaEventRecord(e0, c->stream));
   const double *src = values ? values : c->P.ev.data();
   memcpy(c->h_pinned, src, (size_t)c->P.nz * sizeof(double));
@@ -725,7 +759,6 @@ static int factor_host_rank(chol_t *c, const double *values, double &secs, int &
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0), cudaEventDestroy(e1);
   secs = ms * 1e-3;
   return fetch_info(c, &info);
 }
@@ -743,6 +776,7 @@ int chol_factor_host(chol_t *c, const double *values, int64_t nz, double *diag_o
   const int nr = chol_num_ranks(c);
   std::vector<double> secs(nr, 0.0);
   std::vector<int> info(nr, 0);
+  if (for_ranks(c, [](chol_t *r) { return prepare_rank(r, true, false); })) return -1;
   if (for_ranks(c, [&](chol_t *r) { return factor_host_rank(r, values, secs[r->parent ? r->rank : 0], info[r->parent ? r->rank : 0]); })) return -1;
   double worst = 0;
   int bad = 0;
@@ -928,8 +962,8 @@ int chol_synchronize(chol_t *c) {
 int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops) {
   if (c->parent) return fail(c, "through the group handle");
   if (ensure_device(c)) return -1;
+  if (for_ranks(c, [](chol_t *r) { return prepare_rank(r, false, true); })) return -1;
   if (for_ranks(c, [](chol_t *r) {
-        if (ensure_schedule(r, false)) return -1;
         if (do_assemble(r)) return -1;
         return run_levels(r, r->P.levels - 1, 0, 7, true);
       }))

@@ -295,6 +295,7 @@ int analyze(const Problem &P, Symbolic &S, bool keep, std::string &err) {
     std::vector<Seg>().swap(segs_of[h]);
   }
   S.seg_ptr[N + 1] = (int64_t)S.segs.size();
+  S.poff[N + 1] = off;  // so that [poff[h], poff[h + 1]) is the storage of panel h for every h
   S.total_doubles = off + 4096;  // slack: tile loads may run a few rows past the last panel
   return 0;
 }

@@ -134,7 +134,7 @@ def test_not_positive_definite_is_reported(golden, tmp_path):
         ch.factor()
 
 
-def _entrywise_vs_oracle(grid, tmp_path, threads=8):
+def _entrywise_vs_oracle(grid, tmp_path, threads=8, solve_tol=1e-12):
     """factor a generated grid on the GPU and with the CPU oracle; compare every stored entry and the solve"""
     m, o, c = (str(tmp_path / x) for x in ("a.mtx", "a_ord.txt", "a_clust.txt"))
     ch = Cholesky().generate(*grid)
@@ -150,13 +150,14 @@ def _entrywise_vs_oracle(grid, tmp_path, threads=8):
     assert worst <= 1e-10, worst
     b = np.random.default_rng(0).integers(1, 11, size=ch.n).astype(np.float64)
     x = ch.solve(b)
-    assert np.linalg.norm(b - ch.matvec(x)) <= 1e-12 * np.linalg.norm(b)
+    assert np.linalg.norm(b - ch.matvec(x)) <= solve_tol * np.linalg.norm(b)
     return ch
 
 
 def test_config2_512x512_entrywise(tmp_path):
     """BASELINE config 2 at full size (262 144 unknowns, 1.9e7 factor entries): every entry against the oracle"""
-    _entrywise_vs_oracle((512, 512, 1, 5, 0), tmp_path)
+    # (the solve residual scales with the condition number: ~n for the 2-D Laplacian, 6e-12 measured with either factor)
+    _entrywise_vs_oracle((512, 512, 1, 5, 0), tmp_path, solve_tol=1e-10)
 
 
 def test_config3_64cubed_entrywise(tmp_path):
