@@ -44,7 +44,7 @@ def main():
         agg = collections.OrderedDict()
         bykind = collections.defaultdict(float)
         for l, t in zip(ls, ms):
-            k = (l["kind"] + ("/bcast" if l["shared"] == 1 else "/owned" if l["shared"] == 2 else ""), l["level"],
+            k = (l["kind"] + ("" if l["stream"] == 0 else "/chain" if l["stream"] == 1 else "/background"), l["level"],
                  PHASE.get(l["phase"], str(l["phase"])))
             v = agg.setdefault(k, [0, 0.0, 0.0, 0])
             v[0] += 1
