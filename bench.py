@@ -294,7 +294,7 @@ def main():
     if rank == 0:
         peak, peak_how = fp64_peak()
         gemm_tf = kt["gemm_flops"] / (kt["gemm_ms"] * 1e-3) * 1e-12 if kt["gemm_ms"] > 0 else 0.0
-        tot_ms = kt["potrf_ms"] + kt["trsm_ms"] + kt["gemm_ms"]
+        tot_ms = kt["panel_ms"] + kt["exchange_ms"] + kt["gemm_ms"]
         traffic = ncu_traffic(args.workload) if world == 1 else None
         line = {
             "metric": METRIC, "value": flops / step_s * 1e-9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -310,7 +310,7 @@ def main():
                          "traffic": traffic["traffic"] if traffic else None, "traffic_source": traffic,
                          "peak_source": peak_how,
                          "kernel_share_of_step": kt["gemm_ms"] / tot_ms if tot_ms else None,
-                         "kernel_ms": {k: kt[k] for k in ("potrf_ms", "trsm_ms", "gemm_ms")},
+                         "kernel_ms": {k: kt[k] for k in ("panel_ms", "exchange_ms", "gemm_ms")},
                          "whole_step_frac": flops / step_s * 1e-12 / (peak * world)},
             "roofline_small": small,
             "factor": {"n": ch.n, "nz": ch.nz, "levels": ch.levels, "flops": flops, "factor_GiB": ch.factor_doubles() * 8 / 2**30,

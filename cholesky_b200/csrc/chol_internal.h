@@ -93,15 +93,22 @@ struct TileRef {  // one CTA
   int prob;
   uint16_t tr, tc;
 };
-struct PotrfDesc {  // factor the nb x nb lower tile in place
-  int64_t off;
-  int ld, nb;
-  int col0;  // permuted column of the tile's first column (for info reporting)
-  int pad;
+// One block column (w <= 256 columns starting at column c0) of one panel, factored by ONE launch of panel_kernel:
+// its w x w diagonal block (rows c0 .. c0 + w of the panel) by Cholesky, the rows below by X <- X L^-T.
+// A CTA owns a slab of up to 64 rows for the whole block column; the CTAs that own the diagonal tiles publish
+// them through flag words flag0 .. flag0 + 3 (one per 64-column tile step), the others wait for them.
+// ready != 0: the diagonal block is already factored in memory (rows of a top panel owned by another rank, or
+// the fused_dtrsm phase on its own), nobody waits.
+struct PanelDesc {
+  int64_t off;  // panel base in the factor buffer
+  int ld, c0, w;
+  int col0;     // permuted column of the block column's first column (for info reporting)
+  int flag0, ready;
 };
-struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
-  int64_t l_off, b_off;
-  int ld, nb, rows, pad;
+struct PanelSlab {
+  int desc;
+  int row0, rows;  // stored rows [row0, row0 + rows) of the panel, rows <= 64
+  int t;           // >= 0: this slab is rows c0 + 64 t .. of the diagonal block and factors diagonal tile t; -1: rows below
 };
 
 // One rectangle of a top panel: rows [r0, r0 + rows) x cols [c0, c0 + cols), first entry at factor offset `off`.
@@ -111,18 +118,21 @@ struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T
 struct RectDesc {
   int64_t off;
   int ld, rows, cols, tri0;
+  unsigned mask;  // K_REDUCE: the ranks whose partial sums of this rectangle are not identically zero (plus the owner)
+  int pad;
 };
 
-enum LaunchKind { K_POTRF = 0, K_TRSM = 1, K_GEMM = 2, K_SYNC = 3, K_REDUCE = 4, K_NOP = 5, K_PUSH = 6, K_PANEL = 7 };
+enum LaunchKind { K_PANEL = 0, K_GEMM = 2, K_SYNC = 3, K_REDUCE = 4, K_NOP = 5, K_PUSH = 6 };
 enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
 enum FlagSlot { SLOT_WORLD = 0, SLOT_GROUP = 1, SLOT_DIAG = 2, kFlagSlots = 4 };
 struct Launch {
   int kind;
   int level;
   int phase;
-  int64_t begin, count;  // range in potrf[] / trsm_tiles[] / tiles[] / rects[]
+  int64_t begin, count;  // range in pslabs[] / tiles[] / rects[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
-  int cfg;               // GEMM: 0 = 64x64 CTA tiles on shared-memory operand rings, 3 = one warp per 32x32 tile
+  int cfg;               // GEMM: 0 = 64x64 CTA tiles on shared-memory operand rings, 3 = one warp per 32x32 tile;
+                         // K_PANEL: the widest block column of the launch (sizes its shared memory)
   int stream;            // 0 = update stream, 1 = chain stream (look-ahead), 2 = background pushes
   int wait_ev, rec_ev;   // event to wait for before / to record after the launch (-1: none)
   // multi-GPU (K_PUSH / K_SYNC / K_REDUCE): `mask` = ranks the rectangles are pushed to / reduced from;
@@ -139,14 +149,13 @@ struct Schedule {
   std::vector<GemmProblem> probs;
   std::vector<GemmContrib> contribs;
   std::vector<TileRef> tiles;
-  std::vector<PotrfDesc> potrf;
-  std::vector<TrsmDesc> trsm;
-  std::vector<TileRef> trsm_tiles;  // prob = index into trsm[], tr = slab index
+  std::vector<PanelDesc> pdesc;
+  std::vector<PanelSlab> pslabs;
   std::vector<RectDesc> rects;      // rectangles of K_PUSH / K_REDUCE launches
   std::vector<Launch> launches;
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)
   std::vector<int64_t> a_off;
-  int nb = 64, nbo = 256, slab = 128;
+  int nb = 64, nbo = 256;
   // small fronts: Schur problems with M, N <= small_mn and total K <= small_k run as one warp per 32x32
   // tile (cfg 3, gemm_small_warp): no shared memory, no barriers (CHOL_SMALL_FRONT=0: off)
   bool small_front = true;

@@ -55,9 +55,9 @@ struct chol {
   GemmProblem *d_probs = nullptr;
   GemmContrib *d_contribs = nullptr;
   TileRef *d_tiles = nullptr;
-  PotrfDesc *d_potrf = nullptr;
-  TrsmDesc *d_trsm = nullptr;
-  TileRef *d_trsm_tiles = nullptr;
+  PanelDesc *d_pdesc = nullptr;
+  PanelSlab *d_pslabs = nullptr;
+  int *d_pflags = nullptr;  // four flag words per panel descriptor, zeroed at the start of every run of the level loop
   RectDesc *d_rects = nullptr;
   int *d_info = nullptr;  // [0] first non-positive pivot (1-based permuted column), [1] a peer wait timed out
   int64_t *d_diag_off = nullptr;
@@ -176,7 +176,7 @@ static void free_device(chol_t *c) {
   free_solve(c);
   free_res(c);
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
-  cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects), cudaFree(c->d_info);
+  cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_rects), cudaFree(c->d_info);
   cudaFree(c->d_diag_off), cudaFree(c->d_diag);
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
@@ -358,14 +358,14 @@ static void drop_graph(chol_t *c) {
 }
 static int upload_schedule(chol_t *c) {
   drop_graph(c);  // the captured launches point into the descriptor arrays replaced below
-  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_potrf), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects);
-  c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_potrf = nullptr, c->d_trsm = nullptr, c->d_trsm_tiles = nullptr, c->d_rects = nullptr;
+  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_rects);
+  c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_pdesc = nullptr, c->d_pslabs = nullptr, c->d_pflags = nullptr, c->d_rects = nullptr;
   if (upload(c, &c->d_probs, c->D.probs)) return -100;
   if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
   if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
-  if (upload(c, &c->d_potrf, c->D.potrf)) return -100;
-  if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
-  if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
+  if (upload(c, &c->d_pdesc, c->D.pdesc)) return -100;
+  if (upload(c, &c->d_pslabs, c->D.pslabs)) return -100;
+  CK(cudaMalloc((void **)&c->d_pflags, std::max<size_t>(1, c->D.pdesc.size()) * 4 * sizeof(int)));
   if (upload(c, &c->d_rects, c->D.rects)) return -100;
   return 0;
 }
@@ -410,13 +410,12 @@ static int rank_device(chol_t *c) {  // one rank: streams, buffers, descriptor a
     for (int i = 0; i < c->P.sz[h]; i++) doff[c->P.start[h] + i] = c->S.poff[h] + i + (int64_t)i * c->S.ld[h];
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
-  CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
+  CK(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_bytes(kRowBlock)));
   CK(cudaFuncSetAttribute(gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMain::kSmemBytes));
   {  // load every kernel now: with lazy module loading the first launch of a function synchronises the context, which
      // must not happen while another rank that shares this device is already spinning on a flag
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, potrf_tile));
-    CK(cudaFuncGetAttributes(&fa, trsm_tile));
+    CK(cudaFuncGetAttributes(&fa, panel_kernel));
     CK(cudaFuncGetAttributes(&fa, gemm_small_warp));
     CK(cudaFuncGetAttributes(&fa, gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>));
     CK(cudaFuncGetAttributes(&fa, assemble_kernel));
@@ -484,37 +483,47 @@ static int do_assemble(chol_t *c) {
   return 0;
 }
 
+// One kernel on the stream of the launch being issued.  (Programmatic dependent launch was tried here: every kernel
+// letting its successor be scheduled early and waiting for its predecessor after reading its descriptors.  Measured
+// on B200: 512^2 2.08 -> 2.03 ms, 64^3 23.2 -> 22.8 ms, 128^3 902.6 -> 913.1 ms -- the early-resident CTAs of the chain
+// stream take SM slots from the trailing updates -- and with several ranks on one GPU they starve the rank whose
+// flag they wait for.  Dropped.)
+template <typename... KArgs, typename... Args>
+static void launch(chol_t *c, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, Args... args) {
+  kern<<<grid, block, smem, c->cur>>>(static_cast<KArgs>(args)...);
+}
+
 static int run_launch(chol_t *c, const Launch &l) {
   const unsigned long long flag = (c->run_id << 32) | (unsigned long long)l.seq;
   switch (l.kind) {
-    case K_POTRF:
-      potrf_tile<<<(unsigned)l.count, kPotrfThreads, 0, c->cur>>>(c->d_potrf + l.begin, c->d_fac, c->d_info);
-      break;
-    case K_TRSM:
-      trsm_tile<<<(unsigned)l.count, kSlab, kTrsmSmemBytes, c->cur>>>(c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
+    case K_PANEL:
+      launch(c, panel_kernel, (unsigned)l.count, kPanelThreads, panel_smem_bytes(l.cfg), c->d_pdesc, c->d_pslabs + l.begin, c->d_fac, c->d_pflags,
+             (l.cfg + kNB - 1) / kNB * kNB, c->d_info);
       break;
     case K_GEMM:
       if (l.count <= 0) break;
       if (l.cfg == 3)
-        gemm_small_warp<<<(unsigned)((l.count + kSmallWarps - 1) / kSmallWarps), kSmallWarps * 32, 0, c->cur>>>(
-            c->d_probs, c->d_contribs, c->d_tiles + l.begin, l.count, c->d_fac);
+        launch(c, gemm_small_warp, (unsigned)((l.count + kSmallWarps - 1) / kSmallWarps), kSmallWarps * 32, 0, c->d_probs, c->d_contribs,
+               c->d_tiles + l.begin, l.count, c->d_fac);
       else
-        gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3><<<(unsigned)l.count, GemmMain::kThreads, GemmMain::kSmemBytes, c->cur>>>(
-            c->d_probs, c->d_contribs, c->d_tiles + l.begin, c->d_fac);
+        launch(c, gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>, (unsigned)l.count, GemmMain::kThreads, GemmMain::kSmemBytes, c->d_probs, c->d_contribs,
+               c->d_tiles + l.begin, c->d_fac);
       break;
     case K_SYNC:
-      peer_sync<<<1, 32, 0, c->cur>>>(c->peers, l.slot, flag, l.sig_mask, l.wait_mask, c->d_info + 1);
+      launch(c, peer_sync, 1, 32, 0, c->peers, l.slot, flag, l.sig_mask, l.wait_mask, c->d_info + 1);
       break;
     case K_PUSH:
-      if (l.count > 0 && l.mask)
-        push_rects<<<(unsigned)(l.count * (kRowBlock / kPushCols)), kPushThreads, 0, c->cur>>>(c->d_rects + l.begin, c->d_fac, c->peers, l.mask, l.slot,
-                                                                                             flag, l.sig_mask, c->d_counters + l.stream);
-      else if (l.sig_mask)
-        peer_sync<<<1, 32, 0, c->cur>>>(c->peers, l.slot, flag, l.sig_mask, 0u, c->d_info + 1);
+      if (l.count > 0 && l.mask) {  // enough CTAs per rectangle to spread a small push over about two waves of SMs
+        int cg = 8;
+        while (cg < 64 && l.count * cg < 2 * c->num_sms) cg *= 2;
+        launch(c, push_rects, (unsigned)(l.count * cg), kPushThreads, 0, c->d_rects + l.begin, c->d_fac, c->peers, l.mask, cg, l.slot, flag, l.sig_mask,
+               c->d_counters + l.stream);
+      } else if (l.sig_mask)
+        launch(c, peer_sync, 1, 32, 0, c->peers, l.slot, flag, l.sig_mask, 0u, c->d_info + 1);
       break;
     case K_REDUCE: {
       const int cg = std::max(1, std::min(64, (int)(4 * c->num_sms / std::max<int64_t>(1, l.count))));
-      reduce_rects<<<(unsigned)(l.count * cg), kPushThreads, 0, c->cur>>>(c->d_rects + l.begin, c->d_fac, c->peers, l.mask, cg);
+      launch(c, reduce_rects, (unsigned)(l.count * cg), kPushThreads, 0, c->d_rects + l.begin, c->d_fac, c->peers, l.mask, cg);
       break;
     }
     default:
@@ -551,6 +560,7 @@ static int run_levels(chol_t *c, int lvl_from, int lvl_to, int phase_mask, bool 
   const bool capture = graphable && c->graph_runs >= 1;
   if (graphable) c->graph_runs++;
   if (capture) CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  CK(cudaMemsetAsync(c->d_pflags, 0, std::max<size_t>(1, c->D.pdesc.size()) * 4 * sizeof(int), c->stream));  // no diagonal tile is factored yet
   if (c->D.lookahead) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (int i = 1; i < kStreams; i++) CK(cudaStreamWaitEvent(c->streams[i], c->ev_fork, 0));
@@ -850,19 +860,30 @@ int chol_ipc_import(chol_t *c, const void *all_handles, int world) {
 static chol_t *first_rank(chol_t *c) { return is_group(c) ? c->sub[0] : c; }
 /* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
  * [2] peer-store launches (rows pushed to other ranks), [3] doubles of the top panels (one copy per rank),
- * [4] potrf tiles, [5] trsm slabs.  On a group handle: rank 0 (chol_rank_handle gives the others). */
-int chol_partition_stats(chol_t *c, double *out6) {
+ * [4] diagonal tiles it factors, [5] 64-row slabs it solves, [6] bytes it pulls from peers for the partial-sum reduction, [7] bytes it pushes
+ * to peers per factorization.  On a group handle: rank 0 (chol_rank_handle gives the others). */
+int chol_partition_stats(chol_t *c, double *out8) {
   if (!c->analyzed) return fail(c, "analyze first");
   c = first_rank(c);
-  double a = 0, f = 0, sh = 0, pt = 0, ts = 0;
+  double a = 0, f = 0, sh = 0, pt = 0, ts = 0, pull = 0, pushed = 0;
   for (int64_t o : c->D.a_off) a += (o >= 0);
+  auto bits = [](unsigned m) { return (double)__builtin_popcount(m); };
+  auto area = [](const RectDesc &d) {  // entries at or below the rectangle's diagonal offset
+    double e = 0;
+    for (int r = 0; r < d.rows; r++) e += std::max(0, std::min(d.cols, d.tri0 >= (1 << 29) ? d.cols : d.tri0 + r + 1));
+    return e;
+  };
   for (const Launch &l : c->D.launches) {
     if (l.kind == K_GEMM) f += l.flops;
     if (l.kind == K_PUSH) sh += (l.count > 0 && l.mask);
-    if (l.kind == K_POTRF) pt += (double)l.count;
-    if (l.kind == K_TRSM) ts += (double)l.count;
+    for (int64_t i = l.begin; i < l.begin + l.count && l.kind == K_PANEL; i++) (c->D.pslabs[i].t >= 0 ? pt : ts) += 1.0;
+    for (int64_t i = l.begin; i < l.begin + l.count && (l.kind == K_PUSH || l.kind == K_REDUCE); i++) {
+      const RectDesc &d = c->D.rects[i];
+      if (l.kind == K_PUSH) pushed += 8.0 * area(d) * bits(l.mask);
+      else pull += 8.0 * area(d) * bits(d.mask & l.mask & ~(1u << c->rank));
+    }
   }
-  out6[0] = a, out6[1] = f, out6[2] = sh, out6[3] = (double)c->D.top_doubles, out6[4] = pt, out6[5] = ts;
+  out8[0] = a, out8[1] = f, out8[2] = sh, out8[3] = (double)c->D.top_doubles, out8[4] = pt, out8[5] = ts, out8[6] = pull, out8[7] = pushed;
   return 0;
 }
 /* Algorithmic HBM bytes of one tree level (8 B x distinct clusters read + written, read-modify-
@@ -907,7 +928,7 @@ static int top_diff_rank(chol_t *c, double *out) {
   if (!c->device_ready || !c->factored || !c->peers_ready) return fail(c, "factor first");
   std::vector<RectDesc> rects;
   for (int h = 1; h < (1 << c->D.depth); h++)
-    if (c->P.sz[h] > 0) rects.push_back(RectDesc{c->S.poff[h], c->S.ld[h], c->S.rows[h], c->P.sz[h], 0});
+    if (c->P.sz[h] > 0) rects.push_back(RectDesc{c->S.poff[h], c->S.ld[h], c->S.rows[h], c->P.sz[h], 0, 0u, 0});
   if (rects.empty()) return 0;
   RectDesc *d_r = nullptr;
   unsigned long long *d_w = nullptr, w = 0;
@@ -945,7 +966,7 @@ int chol_get_launch(chol_t *c, int64_t i, int *kind, int *level, int *phase, int
   c = first_rank(c);
   if (i < 0 || i >= (int64_t)c->D.launches.size()) return -1;
   const Launch &l = c->D.launches[i];
-  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = l.cfg | (l.stream << 4);
+  *kind = l.kind, *level = l.level, *phase = l.phase, *ctas = l.count, *flops = l.flops, *cfg = (l.kind == K_GEMM ? l.cfg : 0) | (l.stream << 4) | (l.kind == K_PANEL ? l.cfg << 8 : 0);
   return 0;
 }
 
@@ -959,7 +980,7 @@ int chol_synchronize(chol_t *c) {
 }
 
 /* one instrumented factorization: everything on one stream per rank, CUDA events around every launch */
-int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops) {
+int chol_kernel_times(chol_t *c, double *potrf_ms /* panel_ms */, double *trsm_ms /* exchange_ms */, double *gemm_ms, double *gemm_flops) {
   if (c->parent) return fail(c, "through the group handle");
   if (ensure_device(c)) return -1;
   if (for_ranks(c, [](chol_t *r) { return prepare_rank(r, false, true); })) return -1;
@@ -969,8 +990,8 @@ int chol_kernel_times(chol_t *c, double *potrf_ms, double *trsm_ms, double *gemm
       }))
     return -1;
   chol_t *r = first_rank(c);
-  if (potrf_ms) *potrf_ms = r->k_ms[K_POTRF];
-  if (trsm_ms) *trsm_ms = r->k_ms[K_TRSM];
+  if (potrf_ms) *potrf_ms = r->k_ms[K_PANEL];  // panel_kernel: diagonal blocks and the rows below them
+  if (trsm_ms) *trsm_ms = r->k_ms[K_SYNC] + r->k_ms[K_PUSH] + r->k_ms[K_REDUCE];  // multi-GPU exchange (0 on one GPU)
   if (gemm_ms) *gemm_ms = r->k_ms[K_GEMM];
   if (gemm_flops) *gemm_flops = r->k_gemm_flops;
   return 0;

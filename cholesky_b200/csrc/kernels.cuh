@@ -315,172 +315,228 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmPr
 }
 
 // ---------------------------------------------------------------------------------------------
+// panel_kernel: one 256-wide block column of every panel of a tree level in ONE launch -- LAPACKE_dpotrf of its
+// diagonal block (blas.rg:71) and cblas_dtrsm Right/Lower/Trans/NonUnit of the rows below (blas.rg:99-100).
+//
+// A CTA owns a slab of up to 64 rows for the whole block column and keeps it in shared memory (column-major, row
+// stride 68: conflict-free FP64 MMA fragment loads).  Tile step j = columns 64 j .. 64 j + 63, left-looking:
+//   1. columns j of the slab -= sum_{i<j} (columns i of the slab) x L(j, i)^T   -- 64 x 64 x 64 products on the
+//      tensor cores (DMMA), accumulated in registers over i;
+//   2. the slab that holds diagonal tile j factors it in shared memory (potrf_smem), stores its rows and raises flag
+//      j of the block column; every other slab waits for that flag, loads L(j, j) and solves its 64 x 64 tile
+//      (one row per thread, eight independent FMA chains).
+// So the dependent chain of a block column -- four tile factorizations with a solve and a rank-64 update of the
+// next diagonal tile in between -- runs inside one kernel through flag words in L2 instead of through eleven
+// stream-ordered launches (measured at the root of 128^3: potrf_tile 26 us + trsm_tile 17 us + K = 64 GEMM 18 us per
+// tile step, launch latencies included).  Diagonal slabs come first in the grid, in tile order, so a waiting CTA
+// only ever waits for CTAs that were scheduled before it.
 constexpr int kNB = 64;
+constexpr int kPanelThreads = 256;
+constexpr int kLdx = kNB + 4;
+constexpr long long kSpinLimit = 6000000000LL;  // ~3 s at 2 GHz: a wait gives up and raises an error code instead of hanging the GPU
+inline size_t panel_smem_bytes(int wmax) { return ((size_t)((wmax + kNB - 1) / kNB * kNB) * kLdx + (size_t)kNB * kLdx + kNB) * sizeof(double); }
 
-__device__ __forceinline__ double rsqrt_newton(double s) {
-  // 1/sqrt from the single-precision seed and two Newton steps in double (~2 ulp), as in potrf_tile_w
-  if (s > 1e-30 && s < 1e30) {
-    double r = (double)rsqrtf((float)s);
-    const double hs = 0.5 * s;
-    r = r * (1.5 - hs * r * r);
-    return r * (1.5 - hs * r * r);
-  }
-  return rsqrt(s);
-}
-// potrf_tile: 64 x 64 pivot tile, right-looking and register-resident.  128 threads, thread (i, h) holds columns
-// 32h .. 32h+31 of row i.  Step k: the owners of column k publish it (unscaled) in shared memory, one named
-// barrier, then a_ij -= (a_ik / a_kk) a_jk for the rest of the row and a_ik *= 1/sqrt(a_kk).  One barrier and one
-// rsqrt per column step; the two halves run different (warp-uniform) code.  Entries above the diagonal carry
-// finite garbage that is never stored.  (Measured against the shared-memory left-looking versions of round 1:
-// pivot-tile time of 64^3 5.98 -> 5.03 ms, profiles/experimental_variants_r02.md.)
-__device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-constexpr int kPotrfThreads = 2 * kNB;
-__global__ void __launch_bounds__(kPotrfThreads) potrf_tile(const PotrfDesc *__restrict__ descs, double *__restrict__ fac,
-                                                            int *__restrict__ info) {
-  __shared__ __align__(16) double colbuf[2][kNB];
-  const PotrfDesc d = descs[blockIdx.x];
-  double *__restrict__ A = fac + d.off;
-  const int i = threadIdx.x & (kNB - 1), h = threadIdx.x >> 6, nb = d.nb;
-  constexpr int H = kNB / 2;
-  double a[H];
+// Cholesky of the 64 x 64 tile T (entry (i, c) at T[c * kLdx + i]) in shared memory, right-looking in panels of
+// eight columns.  The 64 dependent column steps are what a tile costs, so they are kept as short as the hardware
+// allows (B200, tools/lat_bench.cu: rsqrt(double) 74 cycles, dependent DFMA 8, a publish through shared memory and
+// a named barrier 56): ONE warp holds the panel in registers, two rows per lane, and does its eight steps with
+// shuffles only -- pivot broadcast, rsqrt, scale, rank-1 update of the remaining panel columns -- then all eight
+// warps apply the rank-8 update to the trailing part.  Columns >= dw are an identity block (steps skipped).
+__device__ __forceinline__ void potrf_smem(double *__restrict__ T, int dw, int col0, int *__restrict__ info) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k0 = 0; k0 < dw; k0 += 8) {
+    if (warp == 0) {
+      double x0[8], x1[8];  // rows lane and lane + 32 of the panel
 #pragma unroll
-  for (int u = 0; u < H; u++) {
-    const int c = h * H + u;
-    a[u] = (i < nb && c <= i) ? A[i + (size_t)c * d.ld] : ((c == i && i >= nb) ? 1.0 : 0.0);
-  }
-  if (h == 0) {
+      for (int j = 0; j < 8; j++) x0[j] = T[(k0 + j) * kLdx + lane], x1[j] = T[(k0 + j) * kLdx + lane + 32];
+      const bool hi = k0 >= 32;  // the panel's own rows k0 .. k0 + 7 sit in x1 (of lanes k0 - 32 ..) or in x0
 #pragma unroll
-    for (int k = 0; k < H; k++) {
-      double *cb = colbuf[k & 1];
-      cb[i] = a[k];
-      bar_sync_128();
-      double p = cb[k];
-      if (!(p > 0.0)) {
-        if (i == k) atomicMin(info, d.col0 + k + 1);
-        p = 1.0;
+      for (int kk = 0; kk < 8; kk++) {
+        double dk = __shfl_sync(0xffffffffu, hi ? x1[kk] : x0[kk], (k0 + kk) & 31);
+        if (!(dk > 0.0)) {
+          if (lane == 0) atomicMin(info, col0 + k0 + kk + 1);  // 1-based permuted column of the first bad pivot
+          dk = 1.0;
+        }
+        const double r = rsqrt(dk);
+        x0[kk] *= r, x1[kk] *= r;  // the pivot row's own entry becomes dk / sqrt(dk); rows above it hold garbage that is never stored
+#pragma unroll
+        for (int j = kk + 1; j < 8; j++) {
+          const double ljk = __shfl_sync(0xffffffffu, hi ? x1[kk] : x0[kk], (k0 + j) & 31);
+          x0[j] = fma(-x0[kk], ljk, x0[j]);
+          x1[j] = fma(-x1[kk], ljk, x1[j]);
+        }
       }
-      const double r = rsqrt_newton(p);
-      const double t = a[k] * (r * r);
-      a[k] *= r;
 #pragma unroll
-      for (int j = k + 1; j < H; j++) a[j] -= t * cb[j];
-    }
-#pragma unroll
-    for (int k = H; k < kNB; k++) bar_sync_128();  // columns 0-31 are final: keep the barrier count of the other half
-  } else {
-#pragma unroll
-    for (int k = 0; k < H; k++) {
-      const double *cb = colbuf[k & 1];
-      bar_sync_128();
-      double p = cb[k];
-      if (!(p > 0.0)) p = 1.0;  // reported by the thread that owns the pivot
-      const double r = rsqrt_newton(p);
-      const double t = cb[i] * (r * r);
-#pragma unroll
-      for (int u = 0; u < H; u += 2) {
-        const double2 c2 = *reinterpret_cast<const double2 *>(&cb[H + u]);
-        a[u] -= t * c2.x;
-        a[u + 1] -= t * c2.y;
+      for (int j = 0; j < 8; j++) {
+        if (lane >= k0 + j) T[(k0 + j) * kLdx + lane] = x0[j];
+        if (lane + 32 >= k0 + j) T[(k0 + j) * kLdx + lane + 32] = x1[j];
       }
     }
+    __syncthreads();
+    const int e0 = k0 + 8;
+    if (e0 < dw) {  // T(i, j) -= sum_k T(i, k) T(j, k) over the panel just factored, i >= j >= e0; thread = row i, every fourth column j
+      const int i = tid & (kNB - 1);
+      double ri[8];
 #pragma unroll
-    for (int k = H; k < kNB; k++) {
-      double *cb = colbuf[k & 1];
-      cb[i] = a[k - H];
-      bar_sync_128();
-      double p = cb[k];
-      if (!(p > 0.0)) {
-        if (i == k) atomicMin(info, d.col0 + k + 1);
-        p = 1.0;
+      for (int k = 0; k < 8; k++) ri[k] = T[(k0 + k) * kLdx + i];
+      for (int j = e0 + (tid >> 6); j < dw; j += kPanelThreads / kNB) {
+        if (j > i) continue;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          s0 = fma(ri[k], T[(k0 + k) * kLdx + j], s0);
+          s1 = fma(ri[k + 1], T[(k0 + k + 1) * kLdx + j], s1);
+        }
+        T[j * kLdx + i] -= s0 + s1;
       }
-      const double r = rsqrt_newton(p);
-      const double t = a[k - H] * (r * r);
-      a[k - H] *= r;
-#pragma unroll
-      for (int j = k + 1; j < kNB; j++) a[j - H] -= t * cb[j];
     }
-  }
-  if (i < nb) {
-#pragma unroll
-    for (int u = 0; u < H; u++)
-      if (h * H + u <= i) A[i + (size_t)(h * H + u) * d.ld] = a[u];
+    __syncthreads();
   }
 }
 
-// 128-row slab per CTA, one row per thread.  The slab (k-major, so a warp reads consecutive words) and
-// L^T live in shared memory; columns are solved eight at a time with eight independent FMA chains, the
-// eight multipliers of one k come as four broadcast vector loads.  Loops are deliberately not fully
-// unrolled: the straight-line version was instruction-fetch bound.
-constexpr int kSlab = 128;
-constexpr int kTrsmSmemBytes = (kNB * kNB + kNB + kNB * kSlab) * 8;
-// All 64 column loads of a slab row are in flight at once (measured: trsm time of 64^3 4.04 -> 3.50 ms against
-// eight rounds of eight).
-__global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
-                                                   double *__restrict__ fac) {
-  extern __shared__ __align__(16) double tsm[];
-  double(*Lt)[kNB] = reinterpret_cast<double(*)[kNB]>(tsm);             // Lt[k][c] = L[c][k]
-  double *rdiag = tsm + kNB * kNB;                                       // 1 / L[c][c]
-  double(*xs)[kSlab] = reinterpret_cast<double(*)[kSlab]>(rdiag + kNB);  // xs[c][row in slab]
-  const TileRef tl = tiles[blockIdx.x];
-  const TrsmDesc d = descs[tl.prob];
-  const int slab = (int)tl.tr | ((int)tl.tc << 16);
-  const int tid = threadIdx.x, nb = d.nb, nb8 = (nb + 7) & ~7;
-  const double *__restrict__ Lg = fac + d.l_off;
-  const int row = slab * kSlab + tid;
-  const bool live = row < d.rows;
-  double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
-  {
-    double v[kNB];
+__global__ void __launch_bounds__(kPanelThreads) panel_kernel(const PanelDesc *__restrict__ descs, const PanelSlab *__restrict__ slabs,
+                                                              double *__restrict__ fac, int *__restrict__ pflags, int wcols, int *__restrict__ info) {
+  extern __shared__ __align__(16) double psm[];
+  double *__restrict__ Xs = psm;                              // the slab: entry (r, c) at Xs[c * kLdx + r]
+  double *__restrict__ Ls = psm + (size_t)wcols * kLdx;       // one tile of L, k-major: Ls[k * kLdx + n] = L(n, k)
+  double *__restrict__ rdiag = Ls + kNB * kLdx;               // 1 / L(n, n) of the diagonal tile in Ls
+  const PanelSlab sl = slabs[blockIdx.x];
+  const PanelDesc d = descs[sl.desc];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncol = sl.t >= 0 ? min(d.w, kNB * (sl.t + 1)) : d.w;  // a diagonal slab ends with its own tile
+  const int nt = (ncol + kNB - 1) / kNB;
+  double *__restrict__ G = fac + d.off + sl.row0 + (size_t)d.c0 * d.ld;         // entry (r, c) of the slab
+  const double *__restrict__ Gd = fac + d.off + d.c0 + (size_t)d.c0 * d.ld;     // entry (n, k) of the diagonal block
+  {  // load: thread = row, every fourth column, eight loads in flight; rows past the slab are zeros and the rows and
+     // columns past a partial diagonal tile an identity block
+    const int r = tid & (kNB - 1), cq = tid >> 6, cload = nt * kNB;
+    for (int cb = cq; cb < cload; cb += 32) {
+      double v[8];
 #pragma unroll
-    for (int c = 0; c < kNB; c++) v[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+      for (int u = 0; u < 8; u++) {
+        const int c = cb + 4 * u;
+        v[u] = (c < ncol && r < sl.rows) ? G[r + (size_t)c * d.ld] : ((sl.t >= 0 && c >= ncol && r == c - kNB * sl.t) ? 1.0 : 0.0);
+      }
 #pragma unroll
-    for (int c = 0; c < kNB; c++) xs[c][tid] = v[c];
-  }
-  {
-    constexpr int PER = kNB * kNB / kSlab;
-    double v[PER];
-#pragma unroll
-    for (int u = 0; u < PER; u++) {
-      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
-      v[u] = (r < nb && c < nb && r >= c) ? Lg[r + (size_t)c * d.ld] : ((r == c) ? 1.0 : 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < PER; u++) {
-      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
-      Lt[c][r] = v[u];
-      if (r == c) rdiag[r] = 1.0 / v[u];
+      for (int u = 0; u < 8; u++)
+        if (cb + 4 * u < cload) Xs[(cb + 4 * u) * kLdx + r] = v[u];
     }
   }
   __syncthreads();
-  if (!live) return;
-  for (int cb = 0; cb < nb8; cb += 8) {
-    double s[8];
+  const int wm = warp & 1, wn = warp >> 1;  // warp tile of a 64 x 64 update: rows 32 wm .., columns 16 wn ..
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int j = 0; j < nt; j++) {
+    const int d0 = j * kNB, dw = min(kNB, d.w - d0);
+    const bool mine = sl.t == j;
+    if (!mine && !d.ready) {  // the tiles L(j, 0 .. j) are final once the slab of diagonal tile j has raised its flag
+      if (tid == 0) {
+        const int *f = pflags + d.flag0 + j;
+        const long long t0 = clock64();
+        int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+          if (v == 0 && clock64() - t0 > kSpinLimit) {
+            atomicExch(info + 1, 2);
+            break;
+          }
+        } while (v == 0);
+      }
+      __syncthreads();
+    }
+    if (j > 0) {
+      double acc[4][2][2];
 #pragma unroll
-    for (int j = 0; j < 8; j++) s[j] = xs[cb + j][tid];
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) acc[mi][ni][e] = Xs[(d0 + 16 * wn + 8 * ni + 2 * t4 + e) * kLdx + 32 * wm + 8 * mi + g];
+      for (int i = 0; i < j; i++) {
+        const double *__restrict__ Bp = Xs + (size_t)(i * kNB) * kLdx;  // the slab of a diagonal tile: L(j, i) is its own rows
+        if (!mine) {
+          __syncthreads();  // the previous tile in Ls has been consumed
+          for (int idx = tid; idx < kNB * kNB; idx += kPanelThreads) {
+            const int n = idx & (kNB - 1), k = idx >> 6;
+            Ls[k * kLdx + n] = n < dw ? Gd[(d0 + n) + (size_t)(i * kNB + k) * d.ld] : 0.0;
+          }
+          __syncthreads();
+          Bp = Ls;
+        }
+        const double *__restrict__ Ap = Xs + (size_t)(i * kNB) * kLdx;
 #pragma unroll 4
-    for (int k = 0; k < cb; k++) {
-      const double xk = xs[k][tid];
-      const double2 *l2 = reinterpret_cast<const double2 *>(&Lt[k][cb]);
+        for (int k4 = 0; k4 < kNB / 4; k4++) {
+          double a[4], b[2];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double2 l = l2[j];
-        s[2 * j] -= xk * l.x;
-        s[2 * j + 1] -= xk * l.y;
+          for (int mi = 0; mi < 4; mi++) a[mi] = -Ap[(4 * k4 + t4) * kLdx + 32 * wm + 8 * mi + g];
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++) b[ni] = Bp[(4 * k4 + t4) * kLdx + 16 * wn + 8 * ni + g];
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) Xs[(d0 + 16 * wn + 8 * ni + 2 * t4 + e) * kLdx + 32 * wm + 8 * mi + g] = acc[mi][ni][e];
+      __syncthreads();
+    }
+    if (mine) {
+      potrf_smem(Xs + (size_t)d0 * kLdx, dw, d.col0 + d0, info);
+      // this slab is done: its tiles left of the diagonal in full, the lower part of the diagonal tile
+      const int r = tid & (kNB - 1);
+      if (r < sl.rows)
+        for (int c = tid >> 6; c < ncol; c += kPanelThreads / kNB)
+          if (c < d0 || r >= c - d0) G[r + (size_t)c * d.ld] = Xs[c * kLdx + r];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(pflags + d.flag0 + j), "r"(1) : "memory");
+      return;
+    }
+    // ---- rows below diagonal tile j: X <- X L(j, j)^-T
+    for (int idx = tid; idx < kNB * kNB; idx += kPanelThreads) {
+      const int n = idx & (kNB - 1), k = idx >> 6;
+      const double v = (n < dw && k <= n) ? Gd[(d0 + n) + (size_t)(d0 + k) * d.ld] : ((n == k) ? 1.0 : 0.0);
+      Ls[k * kLdx + n] = v;
+      if (n == k) rdiag[n] = 1.0 / v;
+    }
+    __syncthreads();
+    if (tid < kNB) {  // one row per thread, eight columns at a time with eight independent FMA chains
+      double *__restrict__ xr = Xs + (size_t)d0 * kLdx + tid;
+      for (int cb = 0; cb < dw; cb += 8) {
+        double sv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) sv[q] = xr[(cb + q) * kLdx];
+#pragma unroll 4
+        for (int k = 0; k < cb; k++) {
+          const double xk = xr[k * kLdx];
+          const double2 *__restrict__ l2 = reinterpret_cast<const double2 *>(&Ls[k * kLdx + cb]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double2 l = l2[q];
+            sv[2 * q] = fma(-xk, l.x, sv[2 * q]);
+            sv[2 * q + 1] = fma(-xk, l.y, sv[2 * q + 1]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+#pragma unroll
+          for (int qq = 0; qq < q; qq++) sv[q] = fma(-sv[qq], Ls[(cb + qq) * kLdx + cb + q], sv[q]);
+          sv[q] *= rdiag[cb + q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) xr[(cb + q) * kLdx] = sv[q];
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-#pragma unroll
-      for (int jj = 0; jj < j; jj++) s[j] -= s[jj] * Lt[cb + jj][cb + j];
-      s[j] *= rdiag[cb + j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) xs[cb + j][tid] = s[j];
+    __syncthreads();
   }
-  for (int c0 = 0; c0 < nb; c0 += 8) {
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (c0 + u < nb) Bp[(size_t)(c0 + u) * d.ld] = xs[c0 + u][tid];
+  {  // rows below the diagonal block: store the whole slab
+    const int r = tid & (kNB - 1);
+    if (r < sl.rows)
+      for (int c = tid >> 6; c < d.w; c += kPanelThreads / kNB) G[r + (size_t)c * d.ld] = Xs[c * kLdx + r];
   }
 }
 
@@ -504,7 +560,6 @@ __global__ void gather_diag_kernel(const int64_t *__restrict__ diag_off, int n, 
 // written only by rank s and only with growing values; a waiter spins with acquire loads on its own words.
 // A wait gives up after kSpinLimit cycles (or as soon as another wait of this GPU has given up) and raises
 // *err, so a lost peer turns into an error code instead of a hung GPU.
-constexpr long long kSpinLimit = 20000000000LL;  // ~10 s at 2 GHz
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
@@ -537,17 +592,21 @@ __global__ void __launch_bounds__(32) peer_sync(Peers peers, int slot, unsigned 
 
 // push_rects: rectangle d (rows x cols, column-major, leading dimension ld, first entry at fac + off) is stored
 // at the same offset into the factor buffer of every rank in `mask`.  One CTA per (rectangle, group of
-// kPushCols columns); rows move as 16-byte pairs (offsets and leading dimensions are even, a trailing odd row
-// takes its padding neighbour along).  tri0 < kNoTriDev: entries with column > tri0 + row are skipped (the
+// columns); rows move as 16-byte pairs (offsets and leading dimensions are even, a trailing odd row
+// takes its padding neighbour along; col_groups CTAs share a rectangle, chosen by the host so that even a single
+// 256 x 256 block spreads over enough SMs to fill the links).  tri0 < kNoTriDev: entries with column > tri0 + row are skipped (the
 // strictly upper part of a diagonal block).  The last CTA to finish raises flag (slot, me) of the ranks in sig.
-constexpr int kPushCols = 32, kPushThreads = 256;
+// One CTA per (rectangle, group of columns).
+constexpr int kPushThreads = 256;
 constexpr int kNoTriDev = 1 << 29;
 __global__ void __launch_bounds__(kPushThreads) push_rects(const RectDesc *__restrict__ rects, double *__restrict__ fac, Peers peers, unsigned mask,
-                                                           int slot, unsigned long long value, unsigned sig, unsigned *__restrict__ counter) {
-  const RectDesc d = rects[blockIdx.x / (kRowBlock / kPushCols)];
-  const int cg = blockIdx.x % (kRowBlock / kPushCols);
+                                                           int col_groups, int slot, unsigned long long value, unsigned sig,
+                                                           unsigned *__restrict__ counter) {
+  const RectDesc d = rects[blockIdx.x / col_groups];
+  const int cg = blockIdx.x % col_groups;
   const int rows2 = (d.rows + 1) / 2;
-  for (int c = cg * kPushCols + (int)threadIdx.x / 128; c < min(d.cols, (cg + 1) * kPushCols); c += kPushThreads / 128) {
+  const int cpg = (d.cols + col_groups - 1) / col_groups;
+  for (int c = cg * cpg + (int)threadIdx.x / 128; c < min(d.cols, (cg + 1) * cpg); c += kPushThreads / 128) {
     for (int r2 = threadIdx.x % 128; r2 < rows2; r2 += 128) {
       if (d.tri0 < kNoTriDev && c > d.tri0 + 2 * r2 + 1) continue;
       const int64_t o = d.off + 2 * r2 + (int64_t)c * d.ld;
@@ -569,11 +628,13 @@ __global__ void __launch_bounds__(kPushThreads) push_rects(const RectDesc *__res
   if (threadIdx.x < 32) signal_and_wait(peers, slot, value, sig, 0u, nullptr);
 }
 
-// reduce_rects: for every rectangle (rows this rank owns of a top panel) the partial sums held by the ranks in
-// `mask` (its group, itself included) are added in ascending rank order and stored into this rank's copy.
-__global__ void __launch_bounds__(kPushThreads) reduce_rects(const RectDesc *__restrict__ rects, double *__restrict__ fac, Peers peers, unsigned mask,
+// reduce_rects: for every rectangle (a block of rows this rank owns of a top panel) the partial sums held by the
+// ranks in the rectangle's mask (those whose subtrees touch it, the owner included) are added in ascending rank
+// order and stored into this rank's copy.
+__global__ void __launch_bounds__(kPushThreads) reduce_rects(const RectDesc *__restrict__ rects, double *__restrict__ fac, Peers peers, unsigned gmask,
                                                              int col_groups) {
   const RectDesc d = rects[blockIdx.x / col_groups];
+  const unsigned mask = d.mask & gmask;
   const int cg = blockIdx.x % col_groups;
   const int rows2 = (d.rows + 1) / 2;
   const int cpg = (d.cols + col_groups - 1) / col_groups;

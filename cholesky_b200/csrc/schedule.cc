@@ -3,18 +3,18 @@
 // Per tree level, leaves first (mmat.rg:1227), three phases that mirror the reference's three
 // __demand(__parallel) loops (mmat.rg:1240, 1259, 1293):
 //   (a) fused_dpotrf  -> blocked Cholesky of every pivot block of the level, in lock step:
-//                        NBO-wide block columns; inside one, NB-wide tiles (tile POTRF, slab TRSM,
-//                        small trailing GEMM); after one, a right-looking grouped GEMM (K = NBO) over
-//                        the whole trailing panel, which keeps the GPU full even for one front.
-//   (b) fused_dtrsm   -> the same blocking applied to the filled off-diagonal rows of the panels
-//                        (by default fused with (a): every row below a pivot tile advances together).
+//                        NBO-wide block columns; one panel_kernel launch factors the diagonal block of
+//                        a block column and solves every row below it (64-row slabs, csrc/kernels.cuh);
+//                        after one, a right-looking grouped GEMM (K = NBO) over the whole trailing
+//                        panel, which keeps the GPU full even for one front.
+//   (b) fused_dtrsm   -> the same launch applied to the filled off-diagonal rows of the panels
+//                        (by default fused with (a): every row below a diagonal block advances together).
 //   (c) fused_dsyrk / fused_dgemm -> one grouped GEMM over DESTINATION clusters: every filled
 //                        cluster (g, p, ia, jb) owns the ordered list of its contributors
 //                        (s ascending), so accumulation is atomic-free and deterministic; the
 //                        extend-add index map is the precomputed destination offset.
 //
-// Look-ahead: the latency-bound chain of a block column (tile POTRF, slab TRSM, K = NB GEMM) runs on
-// a second stream.  The trailing update of block column J is split into the tiles of block column
+// Look-ahead: the latency-bound chain of a block column (panel_kernel) runs on a second stream.  The trailing update of block column J is split into the tiles of block column
 // J + 1 (part A) and the rest (part B); the chain of J + 1 only waits for A, so it overlaps B.
 //
 // Multi-GPU (world = 2^d ranks, one per GPU): rank r owns the subtree under heap index 2^d + r and
@@ -89,6 +89,31 @@ struct Builder {
     if (l.count > 0 || sig) push(l, stream);
   }
 
+  // ---- panel launches (one block column of every panel of the level)
+  std::vector<PanelSlab> pdiag, prows;
+  int pwmax = 0;
+  int add_panel_desc(int64_t off, int ld, int c0, int w, int col0, int ready) {
+    D.pdesc.push_back(PanelDesc{off, ld, c0, w, col0, 4 * (int)D.pdesc.size(), ready});
+    pwmax = std::max(pwmax, w);
+    return (int)D.pdesc.size() - 1;
+  }
+  void add_diag_slabs(int desc) {
+    const PanelDesc &d = D.pdesc[desc];
+    for (int t = 0; t * 64 < d.w; t++) pdiag.push_back(PanelSlab{desc, d.c0 + 64 * t, std::min(64, d.w - 64 * t), t});
+  }
+  void add_row_slabs(int desc, int rb, int re) {
+    for (int r = rb; r < re; r += 64) prows.push_back(PanelSlab{desc, r, std::min(64, re - r), -1});
+  }
+  // diagonal slabs first, in tile order: a slab only ever waits for CTAs earlier in the grid
+  void end_panel(int level, int phase) {
+    std::stable_sort(pdiag.begin(), pdiag.end(), [](const PanelSlab &a, const PanelSlab &b) { return a.t < b.t; });
+    const int64_t b = (int64_t)D.pslabs.size();
+    D.pslabs.insert(D.pslabs.end(), pdiag.begin(), pdiag.end());
+    D.pslabs.insert(D.pslabs.end(), prows.begin(), prows.end());
+    if ((int64_t)D.pslabs.size() > b) push(mk(K_PANEL, level, phase, b, (int64_t)D.pslabs.size() - b, 0, pwmax), 1);
+    pdiag.clear(), prows.clear(), pwmax = 0;
+  }
+
   // ---- grouped GEMM launches
   struct Pending {
     int prob;
@@ -98,7 +123,7 @@ struct Builder {
     int row_tile0 = -1, bcast_tc = 0;
   };
   std::vector<Pending> pend;
-  int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = NB)
+  int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B)
   const TopGroup *own = nullptr;  // mode 1 on a top panel: only the tile rows this rank owns
   void begin_gemm(int m) {
     pend.clear();
@@ -165,9 +190,8 @@ struct Builder {
         }
       flops += pd.flops;
     }
-    const int stream = mode == 2 ? 1 : 0;
-    if (stream == 0) depend(0, 1);
-    push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, stream);
+    depend(0, 1);
+    push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, 0);
   }
   void end_gemm(int level, int phase, bool small_ok) {
     // small fronts (bottom of the tree): one warp per 32x32 tile, operands straight from global memory
@@ -212,12 +236,11 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_SMALL_FRONT")) D.small_front = atoi(e) != 0;
   if (const char *e = getenv("CHOL_SMALL_MN")) D.small_mn = atoi(e);
   if (const char *e = getenv("CHOL_SMALL_K")) D.small_k = atoi(e);
-  if (const char *e = getenv("CHOL_NBO")) D.nbo = std::max(64, atoi(e) / 64 * 64);  // tuning knob: block-column width (single GPU)
+  if (const char *e = getenv("CHOL_NBO")) D.nbo = std::min(256, std::max(64, atoi(e) / 64 * 64));  // tuning knob: block-column width (single GPU)
   if (const char *e = getenv("CHOL_ROW_BLOCK")) D.row_block = std::min(kRowBlock, std::max(64, atoi(e) / 64 * 64));
-  if (world > 1) D.nbo = D.row_block;  // the row blocks of the top panels are block columns
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
-  const int NB = D.nb, SLAB = D.slab, NBO = D.nbo, RB = D.row_block;
+  const int NBO = D.nbo, RB = D.row_block;
   const unsigned wmask = (1u << world) - 1u, me = 1u << rank;
   Builder B(P, S, D);
   auto owner_of = [&](int h) -> int {  // -1: top separator (rows dealt to its group)
@@ -344,51 +367,18 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
         const int phase = which == 0 ? PH_POTRF : which == 1 ? PH_TRSM : (PH_POTRF | PH_TRSM);
         for (int J = 0; J < nouter; J++) {
           const int c0 = J * NBO;
-          for (int jj = 0; jj < NBO / NB; jj++) {
-            const int d0 = c0 + jj * NB;
-            if (d0 >= maxn) break;
-            if (which != 1) {
-              int64_t b = (int64_t)D.potrf.size();
-              for (int h = h0; h < h1; h++) {
-                int n = P.sz[h];
-                if (n <= d0) continue;
-                D.potrf.push_back(PotrfDesc{S.poff[h] + d0 + (int64_t)d0 * S.ld[h], S.ld[h], std::min(NB, n - d0), P.start[h] + d0, 0});
-              }
-              if ((int64_t)D.potrf.size() > b) B.push(Builder::mk(K_POTRF, lvl, phase, b, (int64_t)D.potrf.size() - b), 1);
-            }
-            {
-              int64_t b = (int64_t)D.trsm_tiles.size();
-              for (int h = h0; h < h1; h++) {
-                int n = P.sz[h], ld = S.ld[h];
-                if (n <= d0) continue;
-                int dw = std::min(NB, n - d0);
-                int rbeg = which == 1 ? (n + 1) / 2 * 2 : d0 + dw;
-                int rend = which == 0 ? n : S.rows[h];
-                if (rend <= rbeg) continue;
-                D.trsm.push_back(TrsmDesc{S.poff[h] + d0 + (int64_t)d0 * ld, S.poff[h] + rbeg + (int64_t)d0 * ld, ld, dw, rend - rbeg, 0});
-                int ns = (rend - rbeg + SLAB - 1) / SLAB;
-                for (int s = 0; s < ns; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(s & 0xffff), (uint16_t)(s >> 16)});
-              }
-              if ((int64_t)D.trsm_tiles.size() > b) B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
-            }
-            // right-looking update of the rest of this block column (K = NB)
-            B.begin_gemm(2);
-            for (int h = h0; h < h1; h++) {
-              int n = P.sz[h], ld = S.ld[h];
-              if (n <= d0) continue;
-              int dw = std::min(NB, n - d0), e0 = d0 + dw, cend = std::min(c0 + NBO, n);
-              if (e0 >= cend) continue;
-              int64_t base = S.poff[h];
-              if (which != 1)
-                B.add_problem(base + e0 + (int64_t)e0 * ld, ld, (which == 0 ? n : S.rows[h]) - e0, cend - e0, 1, base + e0 + (int64_t)d0 * ld,
-                              base + e0 + (int64_t)d0 * ld, ld, ld, dw);
-              else {
-                int r0 = (n + 1) / 2 * 2, m = S.rows[h] - r0;
-                B.add_problem(base + r0 + (int64_t)e0 * ld, ld, m, cend - e0, 0, base + r0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
-              }
-            }
-            B.end_gemm(lvl, phase, false);
+          // the block column of every panel of the level: diagonal block + the rows below it, one launch
+          for (int h = h0; h < h1; h++) {
+            const int n = P.sz[h];
+            if (n <= c0) continue;
+            const int w = std::min(NBO, n - c0), c1 = c0 + w, r0 = (n + 1) / 2 * 2;
+            const int desc = B.add_panel_desc(S.poff[h], S.ld[h], c0, w, P.start[h] + c0, which == 1 ? 1 : 0);
+            if (which != 1) B.add_diag_slabs(desc);
+            if (which == 0) B.add_row_slabs(desc, c1, n);
+            else if (which == 1) B.add_row_slabs(desc, r0, S.rows[h]);
+            else B.add_row_slabs(desc, c1 < n ? c1 : r0, S.rows[h]);
           }
+          B.end_panel(lvl, phase);
           // right-looking update of everything to the right of block column J (K = NBO)
           B.begin_gemm(1);
           for (int h = h0; h < h1; h++) {
@@ -431,47 +421,25 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           const int rb = std::max(b * RB, below0), re = std::min((b + 1) * RB, R);
           if (re > rb) mine.push_back({rb, re});
         }
-        if (rank == diag_owner) {
-          // the diagonal block (w x w), tile by tile: POTRF, TRSM of the rows below inside the block, K = NB update
-          for (int d0 = c0; d0 < c1; d0 += NB) {
-            const int dw = std::min(NB, c1 - d0), e0 = d0 + dw;
-            D.potrf.push_back(PotrfDesc{base + d0 + (int64_t)d0 * ld, ld, dw, P.start[p] + d0, 0});
-            B.push(Builder::mk(K_POTRF, lvl, phase, (int64_t)D.potrf.size() - 1, 1), 1);
-            if (e0 >= c1) continue;
-            int64_t b = (int64_t)D.trsm_tiles.size();
-            D.trsm.push_back(TrsmDesc{base + d0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, dw, c1 - e0, 0});
-            for (int s = 0; s < (c1 - e0 + SLAB - 1) / SLAB; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)s, 0});
-            B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
-            B.begin_gemm(2);
-            B.add_problem(base + e0 + (int64_t)e0 * ld, ld, c1 - e0, c1 - e0, 1, base + e0 + (int64_t)d0 * ld, base + e0 + (int64_t)d0 * ld, ld, ld, dw);
-            B.end_gemm(lvl, phase, false);
-          }
+        if (rank == diag_owner) {  // the diagonal block (w x w), then out to every rank
+          B.add_diag_slabs(B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 0));
+          B.end_panel(lvl, phase);
           int64_t rb = (int64_t)D.rects.size();
-          D.rects.push_back(RectDesc{base + c0 + (int64_t)c0 * ld, ld, w, w, 0});
+          D.rects.push_back(RectDesc{base + c0 + (int64_t)c0 * ld, ld, w, w, 0, 0u, 0});
           B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + J + 1, gmask & ~me, 1);
         } else
           B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
-        // own rows below: X <- X L_JJ^-T, 64 columns at a time
-        for (int d0 = c0; d0 < c1 && !mine.empty(); d0 += NB) {
-          const int dw = std::min(NB, c1 - d0), e0 = d0 + dw;
-          int64_t b = (int64_t)D.trsm_tiles.size();
-          for (auto &rg : mine) {
-            D.trsm.push_back(TrsmDesc{base + d0 + (int64_t)d0 * ld, base + rg.first + (int64_t)d0 * ld, ld, dw, rg.second - rg.first, 0});
-            for (int s = 0; s < (rg.second - rg.first + SLAB - 1) / SLAB; s++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)s, 0});
-          }
-          B.push(Builder::mk(K_TRSM, lvl, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
-          if (e0 >= c1) continue;
-          B.begin_gemm(2);
-          for (auto &rg : mine)
-            B.add_problem(base + rg.first + (int64_t)e0 * ld, ld, rg.second - rg.first, c1 - e0, 0, base + rg.first + (int64_t)d0 * ld,
-                          base + e0 + (int64_t)d0 * ld, ld, ld, dw);
-          B.end_gemm(lvl, phase, false);
+        // own rows below: X <- X L_JJ^-T (the diagonal block is final in this rank's copy by now)
+        if (!mine.empty()) {
+          const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
+          for (auto &rg : mine) B.add_row_slabs(desc, rg.first, rg.second);
+          B.end_panel(lvl, phase);
         }
         // the group needs the pivot-block rows of this block column for its trailing updates: push them now ...
         {
           int64_t rb = (int64_t)D.rects.size();
           for (auto &rg : mine)
-            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri});
+            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
           B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 1);
         }
         // ... and, in the background, everything else to everybody (needed from the end of the level on)
@@ -479,11 +447,11 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           B.depend(2, 1);
           int64_t rb = (int64_t)D.rects.size();
           for (auto &rg : mine)
-            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri});
+            if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
           B.push_rects(lvl, phase, rb, wmask & ~gmask, 0, 0, 0, 2);
           rb = (int64_t)D.rects.size();
           for (auto &rg : mine)
-            if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri});
+            if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri, 0u, 0});
           B.push_rects(lvl, phase, rb, wmask & ~me, 0, 0, 0, 2);
         }
         // trailing update of this rank's rows (K = w); its B operand is the group's pushed rows
@@ -541,19 +509,65 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
     }
     B.end_gemm(lvl, PH_UPDATE, !top);
 
-    // the subtrees are done: every rank sums, for the rows it owns in each top panel above its subtree, the
-    // partial sums of that panel's group (the strictly upper part of a pivot block is never touched)
+    // The subtrees are done: every rank sums, for the rows it owns in each top panel above its subtree, the
+    // partial sums of that panel's group.  A subtree touches only the part of the top panels that borders its
+    // box, so the sum is taken block by block (row block x column block of the panel) over the ranks whose
+    // subtrees have a Schur destination in that block, and blocks nobody else touched are left alone; the
+    // strictly upper part of a pivot block is never touched at all.
     if (world > 1 && lvl == depth) {
       B.depend(0, 1);
       B.sync(lvl, PH_UPDATE, SLOT_WORLD, 1, wmask & ~me, wmask & ~me, 0);
+      // touched[lv][rb * ncb + cb]: ranks with a contribution to block (rb, cb) of this rank's level-lv panel
+      std::vector<std::vector<unsigned>> touched(depth);
+      std::vector<int> ncbs(depth, 0);
+      for (int lv = 0; lv < depth; lv++) {
+        const int p = ((1 << depth) + rank) >> (depth - lv);
+        ncbs[lv] = (P.sz[p] + RB - 1) / RB;
+        touched[lv].assign((size_t)((S.rows[p] + RB - 1) / RB) * std::max(1, ncbs[lv]), 0u);
+      }
+      std::vector<std::vector<std::vector<unsigned>>> part(host_threads(), touched);
+      parallel_chunks((int64_t)N - (1 << depth) + 1, [&](int64_t i0, int64_t i1, int wk) {
+        auto &mine = part[wk];
+        for (int64_t hi = i0; hi < i1; hi++) {
+          const int hs = (1 << depth) + (int)hi;  // every separator below the top levels
+          const int q = owner_of(hs);
+          if (q == rank) continue;  // this rank's own partial sums are already in its copy
+          const int64_t s0 = S.seg_ptr[hs] + 1, s1 = S.seg_ptr[hs + 1];
+          for (int64_t j = s0; j < s1; j++) {
+            const Seg &b = S.segs[j];
+            const int p = b.anc, lv = P.level_of(p);
+            if (lv >= depth || p != (((1 << depth) + rank) >> (depth - lv))) continue;  // not a top panel above this rank
+            const TopGroup grp = top_group(p, lv, depth, RB);
+            for (int64_t i = j; i < s1; i++) {
+              const Seg &a = S.segs[i];
+              const int crow = locate(p, P.start[a.anc] + a.lo);
+              if (crow < 0) continue;  // (reported by the Schur pass of the owning rank)
+              for (int rb = crow / RB; rb <= (crow + a.hi - a.lo - 1) / RB; rb++) {
+                if (grp.owner(rb) != rank) continue;
+                for (int cb = b.lo / RB; cb <= (b.hi - 1) / RB; cb++) mine[lv][(size_t)rb * ncbs[lv] + cb] |= 1u << q;
+              }
+            }
+          }
+        }
+      });
+      for (auto &pt : part)
+        for (int lv = 0; lv < depth; lv++)
+          for (size_t i = 0; i < touched[lv].size(); i++) touched[lv][i] |= pt[lv][i];
       for (int lv = depth - 1; lv >= 0; lv--) {
         const int p = ((1 << depth) + rank) >> (depth - lv);
         const TopGroup grp = top_group(p, lv, depth, RB);
-        const int R = S.rows[p];
-        int64_t rb = (int64_t)D.rects.size();
-        for (int b = 0; b * RB < R; b++)
-          if (grp.owner(b) == rank) D.rects.push_back(RectDesc{S.poff[p] + b * RB, S.ld[p], std::min(RB, R - b * RB), P.sz[p], b * RB});
-        Launch l = Builder::mk(K_REDUCE, lvl, PH_UPDATE, rb, (int64_t)D.rects.size() - rb);
+        const int R = S.rows[p], n = P.sz[p];
+        int64_t rb0 = (int64_t)D.rects.size();
+        for (int rb = 0; rb * RB < R; rb++) {
+          if (grp.owner(rb) != rank) continue;
+          for (int cb = 0; cb * RB < n; cb++) {
+            const unsigned m = touched[lv][(size_t)rb * ncbs[lv] + cb];
+            const int r0b = rb * RB, c0b = cb * RB, rows = std::min(RB, R - r0b);
+            if (!m || (r0b < n && r0b + rows - 1 < c0b)) continue;  // nobody else contributed / wholly above the diagonal
+            D.rects.push_back(RectDesc{S.poff[p] + r0b + (int64_t)c0b * S.ld[p], S.ld[p], rows, std::min(RB, n - c0b), r0b - c0b, m | me, 0});
+          }
+        }
+        Launch l = Builder::mk(K_REDUCE, lvl, PH_UPDATE, rb0, (int64_t)D.rects.size() - rb0);
         l.mask = grp.mask();
         if (l.count > 0) B.push(l, 0);
       }

@@ -179,7 +179,7 @@ class Cholesky:
     def kernel_times(self):
         a, b, c, f = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self._ck(self.L.chol_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
-        return dict(potrf_ms=a.value, trsm_ms=b.value, gemm_ms=c.value, gemm_flops=f.value)
+        return dict(panel_ms=a.value, exchange_ms=b.value, gemm_ms=c.value, gemm_flops=f.value)
 
     # ---- multi-GPU: one process and one handle per GPU (see cholesky_b200/distributed.py)
     def set_partition(self, rank, world):
@@ -198,10 +198,11 @@ class Cholesky:
         self._ck(self.L.chol_ipc_import(self.h, buf, world))
 
     def partition_stats(self):
-        out = np.zeros(6, dtype=np.float64)
+        out = np.zeros(8, dtype=np.float64)
         self._ck(self.L.chol_partition_stats(self.h, _p(out)))
         return dict(assembled=int(out[0]), gemm_flops=float(out[1]), push_launches=int(out[2]),
-                    top_doubles=int(out[3]), potrf_tiles=int(out[4]), trsm_slabs=int(out[5]))
+                    top_doubles=int(out[3]), diag_tiles=int(out[4]), row_slabs=int(out[5]),
+                    reduce_pull_bytes=float(out[6]), push_bytes=float(out[7]))
 
     def top_copies_diff(self):
         """largest |difference| between the ranks' copies of the factored top panels (0 = bit-identical)"""
@@ -224,9 +225,9 @@ class Cholesky:
         for i in range(int(self.L.chol_num_launches(self.h))):
             self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
                                    C.byref(ctas), C.byref(flops), C.byref(cfg))
-            names = ("potrf_tile", "trsm_tile", "gemm_grouped", "peer_sync", "reduce_rects", "nop", "push_rects", "panel")
+            names = ("panel_kernel", "-", "gemm_grouped", "peer_sync", "reduce_rects", "nop", "push_rects")
             out.append(dict(kind=names[kind.value], level=level.value, phase=phase.value, ctas=ctas.value,
-                            flops=flops.value, cfg=cfg.value & 15, stream=cfg.value >> 4))
+                            flops=flops.value, cfg=cfg.value & 15, stream=(cfg.value >> 4) & 15, width=cfg.value >> 8))
         return out
 
     # ---- results (mmat.rg:1360-1362)

@@ -107,14 +107,17 @@ int chol_fused_update(chol_t *, int lvl);
  * factor, and read back diag(L) in permuted order.  values may be NULL (reuse the loaded ones). */
 int chol_factor_host(chol_t *, const double *values, int64_t nz, double *diag_out, chol_stats_t *stats);
 int chol_synchronize(chol_t *);
-/* the compiled launch list: kind 0 potrf_tile / 1 trsm_tile / 2 gemm_grouped / 3 peer_sync / 4 reduce_rects /
- * 5 (no kernel: a cross-stream dependency) / 6 push_rects, tree level, phase (1 fused_dpotrf, 2 fused_dtrsm,
- * 4 fused_dsyrk+dgemm), CTAs or rectangles, executed flops, cfg = GEMM kernel (0: 64x64 tiles, 3: warp tiles)
- * + 16 * stream (0 update, 1 chain, 2 background pushes) */
+/* the compiled launch list: kind 0 panel_kernel (diagonal block of a block column + the rows below it) /
+ * 2 gemm_grouped / 3 peer_sync / 4 reduce_rects / 5 (no kernel: a cross-stream dependency) / 6 push_rects, tree
+ * level, phase (1 fused_dpotrf, 2 fused_dtrsm, 4 fused_dsyrk+dgemm), CTAs or rectangles, executed flops,
+ * cfg = GEMM kernel (0: 64x64 tiles, 3: warp tiles) + 16 * stream (0 update, 1 chain, 2 background pushes)
+ * + 256 * widest block column of a panel launch */
 int64_t chol_num_launches(chol_t *);
 int chol_get_launch(chol_t *, int64_t i, int *kind, int *level, int *phase, int64_t *ctas, double *flops, int *cfg);
-/* per-kernel accounting of the last chol_factor (device time by kernel class, ms per iteration) */
-int chol_kernel_times(chol_t *, double *potrf_ms, double *trsm_ms, double *gemm_ms, double *gemm_flops);
+/* per-kernel accounting of one instrumented factorization (device time by kernel class, ms): panel_kernel
+ * (fused_dpotrf + fused_dtrsm of the block columns), the multi-GPU exchange kernels (0 on one GPU), the grouped
+ * GEMM (fused_dsyrk + fused_dgemm and the in-panel trailing updates) and the flops the latter executed */
+int chol_kernel_times(chol_t *, double *panel_ms, double *exchange_ms, double *gemm_ms, double *gemm_flops);
 /* per-launch device time (ms) of that instrumented pass, in launch-list order; returns the count */
 int64_t chol_launch_times(chol_t *, float *ms, int64_t cap);
 
@@ -131,8 +134,10 @@ int chol_set_partition(chol_t *, int rank, int world);
 int chol_ipc_export(chol_t *, void *handles128);
 int chol_ipc_import(chol_t *, const void *all_handles, int world);
 /* what this rank's schedule covers: [0] matrix entries it assembles, [1] GEMM flops it executes,
- * [2] peer-store launches (rows pushed to other ranks), [3] doubles of the top panels, [4] potrf tiles, [5] trsm slabs */
-int chol_partition_stats(chol_t *, double *out6);
+ * [2] peer-store launches (rows pushed to other ranks), [3] doubles of the top panels, [4] diagonal tiles it factors,
+ * [5] 64-row slabs it solves,
+ * [6] bytes it pulls from peers for the partial-sum reduction, [7] bytes it pushes to peers, per factorization */
+int chol_partition_stats(chol_t *, double *out8);
 int chol_rank(chol_t *);
 int chol_world(chol_t *);
 /* verification: largest |difference| between the ranks' copies of the factored top panels, compared on the GPUs

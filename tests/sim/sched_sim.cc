@@ -97,18 +97,25 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
     Rank &k = R[me];
     double *fac = k.fac.data();
     switch (l.kind) {
-      case K_POTRF:
-        for (int64_t i = l.begin; i < l.begin + l.count; i++) {
-          const PotrfDesc &d = k.D.potrf[i];
-          potrf(fac + d.off, d.ld, d.nb, bad_pivot);
-        }
-        break;
-      case K_TRSM:
-        for (int64_t i = l.begin; i < l.begin + l.count; i++) {
-          const TileRef &t = k.D.trsm_tiles[i];
-          const TrsmDesc &d = k.D.trsm[t.prob];
-          const int slab = (int)t.tr | ((int)t.tc << 16);
-          trsm(fac + d.l_off, fac + d.b_off, d.ld, d.nb, slab * 128, std::min(d.rows, (slab + 1) * 128));
+      case K_PANEL:  // slabs in grid order: a slab only depends on diagonal slabs that precede it
+        for (int64_t si = l.begin; si < l.begin + l.count; si++) {
+          const PanelSlab &sl = k.D.pslabs[si];
+          const PanelDesc &d = k.D.pdesc[sl.desc];
+          double *G = fac + d.off + sl.row0 + (size_t)d.c0 * d.ld;            // entry (r, c) of the slab
+          const double *Gd = fac + d.off + d.c0 + (size_t)d.c0 * d.ld;        // entry (n, kk) of the diagonal block
+          const int ncol = sl.t >= 0 ? std::min(d.w, 64 * (sl.t + 1)) : d.w;
+          for (int j = 0; j * 64 < ncol; j++) {
+            const int d0 = 64 * j, dw = std::min(64, d.w - d0);
+            for (int c = 0; c < dw; c++)  // left-looking update from the tile columns before j
+              for (int r = 0; r < sl.rows; r++) {
+                if (sl.t == j && r < c) continue;  // strictly upper part of the diagonal tile: never used
+                double acc = 0;
+                for (int kk = 0; kk < d0; kk++) acc += G[r + (size_t)kk * d.ld] * Gd[(d0 + c) + (size_t)kk * d.ld];
+                G[r + (size_t)(d0 + c) * d.ld] -= acc;
+              }
+            if (sl.t == j) potrf(G + (size_t)d0 * d.ld, d.ld, dw, bad_pivot);
+            else trsm(Gd + d0 + (size_t)d0 * d.ld, G + (size_t)d0 * d.ld, d.ld, dw, 0, sl.rows);
+          }
         }
         break;
       case K_GEMM: {
@@ -157,7 +164,7 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
               const int64_t o = d.off + 2 * r2 + (int64_t)c * d.ld;
               double s0 = 0, s1 = 0;
               for (int p = 0; p < world; p++)
-                if ((l.mask >> p) & 1u) s0 += R[p].fac[o], s1 += R[p].fac[o + 1];
+                if ((l.mask & d.mask) >> p & 1u) s0 += R[p].fac[o], s1 += R[p].fac[o + 1];
               fac[o] = s0, fac[o + 1] = s1;
             }
         }

@@ -25,6 +25,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["CHOL_ROW_BLOCK"] = "64"   # deal the rows of this small grid's top panels in blocks of 64
+    os.environ["CHOL_NBO"] = "64"         # ... and block every other panel (and the single-rank schedule) the same way
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cholesky_b200 import Cholesky
@@ -68,13 +69,12 @@ def test_partition_covers_single_rank_schedule(world):
 
     sub = lambda l: l["level"] >= depth      # noqa: E731
     top = lambda l: l["level"] < depth       # noqa: E731
-    for kind, key in (("gemm_grouped", "flops"), ("potrf_tile", "ctas"), ("trsm_tile", "ctas")):
+    for kind, key in (("gemm_grouped", "flops"), ("panel_kernel", "ctas")):
         # subtree levels: split with no overlap
         assert sum(total(r["launches"], kind, key, sub) for r in ranks) == pytest.approx(
             total(single["launches"], kind, key, sub), rel=1e-12)
     # top levels: every pivot tile is factored by exactly one rank (the owner of its diagonal block) ...
-    # (the single-GPU schedule blocks by 256 columns, the partitioned one by the row block; tiles are 64 wide in both)
-    assert sum(total(r["launches"], "potrf_tile", "ctas", top) for r in ranks) == total(single["launches"], "potrf_tile", "ctas", top)
+    assert sum(r["stats"]["diag_tiles"] for r in ranks) == single["stats"]["diag_tiles"]
     # ... and the executed flops of the top levels are those of the single-rank schedule, dealt out with no overlap
     # (a few masked rows at odd ownership boundaries and the per-tile accounting of split launches aside)
     split_flops = sum(total(r["launches"], "gemm_grouped", "flops", top) for r in ranks)
@@ -89,7 +89,7 @@ def test_partition_covers_single_rank_schedule(world):
         assert r["stats"]["push_launches"] > 0
         assert r["stats"]["top_doubles"] == ranks[0]["stats"]["top_doubles"] > 0
         # streams: chain kernels on 1, background pushes on 2, everything else on 0
-        assert {l["stream"] for l in r["launches"] if l["kind"] == "potrf_tile"} == {1}
+        assert {l["stream"] for l in r["launches"] if l["kind"] == "panel_kernel"} == {1}
         assert {l["stream"] for l in r["launches"] if l["kind"] == "reduce_rects"} == {0}
     nsync = [sum(l["kind"] == "peer_sync" for l in r["launches"]) for r in ranks]
     assert min(nsync) >= 2 + depth

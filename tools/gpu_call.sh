@@ -1,4 +1,1 @@
-mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/smoke.log; cat gpurun_out/pytest_gpu.log
+tools/potrf_bench
