@@ -105,6 +105,10 @@ struct PanelDesc {
   int col0;     // permuted column of the block column's first column (for info reporting)
   int flag0, ready;
 };
+struct TrsmDesc {  // rows x nb slab below a factored tile: B <- B * L^-T (trsm_tile, 128-row slabs)
+  int64_t l_off, b_off;
+  int ld, nb, rows, pad;
+};
 struct PanelSlab {
   int desc;
   int row0, rows;  // stored rows [row0, row0 + rows) of the panel, rows <= 64
@@ -122,14 +126,14 @@ struct RectDesc {
   int pad;
 };
 
-enum LaunchKind { K_PANEL = 0, K_GEMM = 2, K_SYNC = 3, K_REDUCE = 4, K_NOP = 5, K_PUSH = 6 };
+enum LaunchKind { K_PANEL = 0, K_TRSM = 1, K_GEMM = 2, K_SYNC = 3, K_REDUCE = 4, K_NOP = 5, K_PUSH = 6 };
 enum Phase { PH_POTRF = 1, PH_TRSM = 2, PH_UPDATE = 4 };  // which reference fused task the launch belongs to
 enum FlagSlot { SLOT_WORLD = 0, SLOT_GROUP = 1, SLOT_DIAG = 2, kFlagSlots = 4 };
 struct Launch {
   int kind;
   int level;
   int phase;
-  int64_t begin, count;  // range in pslabs[] / tiles[] / rects[]
+  int64_t begin, count;  // range in pslabs[] / trsm_tiles[] / tiles[] / rects[]
   double flops;          // executed flops (for per-kernel accounting), GEMM only
   int cfg;               // GEMM: 0 = 64x64 CTA tiles on shared-memory operand rings, 3 = one warp per 32x32 tile;
                          // K_PANEL: the widest block column of the launch (sizes its shared memory)
@@ -151,6 +155,15 @@ struct Schedule {
   std::vector<TileRef> tiles;
   std::vector<PanelDesc> pdesc;
   std::vector<PanelSlab> pslabs;
+  std::vector<TrsmDesc> trsm;
+  std::vector<TileRef> trsm_tiles;  // prob = index into trsm[], tr = slab index
+  // The rows below the diagonal blocks of a launch go through panel_kernel's slabs (one launch, lowest latency)
+  // when there are at most this many 64-row slabs, and through trsm_tile + grouped GEMM launches per 64-column
+  // tile step (highest throughput) when there are more.  Measured on one B200 (128^3 / 64^3): always slabs
+  // 958 / 24.2 ms, <= 296 slabs 906 / 23.2 ms, <= 64 slabs 903 / 23.0 ms.  On the top levels of a partition the
+  // chain of a block column is the critical path of the whole group, so slabs are used up to two waves of CTAs.
+  // (CHOL_FUSED_ROWS_MAX / CHOL_FUSED_ROWS_MAX_TOP)
+  int fused_rows_max = 64, fused_rows_max_top = 296;
   std::vector<RectDesc> rects;      // rectangles of K_PUSH / K_REDUCE launches
   std::vector<Launch> launches;
   // assembly: value e of the input goes to factor[a_off[e]] (-1: dropped, mmat.rg:1191)

@@ -57,6 +57,8 @@ struct chol {
   TileRef *d_tiles = nullptr;
   PanelDesc *d_pdesc = nullptr;
   PanelSlab *d_pslabs = nullptr;
+  TrsmDesc *d_trsm = nullptr;
+  TileRef *d_trsm_tiles = nullptr;
   int *d_pflags = nullptr;  // four flag words per panel descriptor, zeroed at the start of every run of the level loop
   RectDesc *d_rects = nullptr;
   int *d_info = nullptr;  // [0] first non-positive pivot (1-based permuted column), [1] a peer wait timed out
@@ -176,7 +178,7 @@ static void free_device(chol_t *c) {
   free_solve(c);
   free_res(c);
   cudaFree(c->d_fac), cudaFree(c->d_vals), cudaFree(c->d_aoff), cudaFree(c->d_probs), cudaFree(c->d_contribs);
-  cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_rects), cudaFree(c->d_info);
+  cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects), cudaFree(c->d_info);
   cudaFree(c->d_diag_off), cudaFree(c->d_diag);
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
@@ -358,13 +360,16 @@ static void drop_graph(chol_t *c) {
 }
 static int upload_schedule(chol_t *c) {
   drop_graph(c);  // the captured launches point into the descriptor arrays replaced below
-  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_rects);
+  cudaFree(c->d_probs), cudaFree(c->d_contribs), cudaFree(c->d_tiles), cudaFree(c->d_pdesc), cudaFree(c->d_pslabs), cudaFree(c->d_pflags), cudaFree(c->d_trsm), cudaFree(c->d_trsm_tiles), cudaFree(c->d_rects);
+  c->d_trsm = nullptr, c->d_trsm_tiles = nullptr;
   c->d_probs = nullptr, c->d_contribs = nullptr, c->d_tiles = nullptr, c->d_pdesc = nullptr, c->d_pslabs = nullptr, c->d_pflags = nullptr, c->d_rects = nullptr;
   if (upload(c, &c->d_probs, c->D.probs)) return -100;
   if (upload(c, &c->d_contribs, c->D.contribs)) return -100;
   if (upload(c, &c->d_tiles, c->D.tiles)) return -100;
   if (upload(c, &c->d_pdesc, c->D.pdesc)) return -100;
   if (upload(c, &c->d_pslabs, c->D.pslabs)) return -100;
+  if (upload(c, &c->d_trsm, c->D.trsm)) return -100;
+  if (upload(c, &c->d_trsm_tiles, c->D.trsm_tiles)) return -100;
   CK(cudaMalloc((void **)&c->d_pflags, std::max<size_t>(1, c->D.pdesc.size()) * 4 * sizeof(int)));
   if (upload(c, &c->d_rects, c->D.rects)) return -100;
   return 0;
@@ -411,11 +416,13 @@ static int rank_device(chol_t *c) {  // one rank: streams, buffers, descriptor a
   if (upload(c, &c->d_diag_off, doff)) return -100;
   CK(cudaMalloc((void **)&c->d_diag, std::max(1, c->P.n) * sizeof(double)));
   CK(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_bytes(kRowBlock)));
+  CK(cudaFuncSetAttribute(trsm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmemBytes));
   CK(cudaFuncSetAttribute(gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMain::kSmemBytes));
   {  // load every kernel now: with lazy module loading the first launch of a function synchronises the context, which
      // must not happen while another rank that shares this device is already spinning on a flag
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, panel_kernel));
+    CK(cudaFuncGetAttributes(&fa, trsm_tile));
     CK(cudaFuncGetAttributes(&fa, gemm_small_warp));
     CK(cudaFuncGetAttributes(&fa, gemm_grouped_ws<64, 64, 16, 32, 32, 4, 3>));
     CK(cudaFuncGetAttributes(&fa, assemble_kernel));
@@ -499,6 +506,9 @@ static int run_launch(chol_t *c, const Launch &l) {
     case K_PANEL:
       launch(c, panel_kernel, (unsigned)l.count, kPanelThreads, panel_smem_bytes(l.cfg), c->d_pdesc, c->d_pslabs + l.begin, c->d_fac, c->d_pflags,
              (l.cfg + kNB - 1) / kNB * kNB, c->d_info);
+      break;
+    case K_TRSM:
+      launch(c, trsm_tile, (unsigned)l.count, kSlab, kTrsmSmemBytes, c->d_trsm, c->d_trsm_tiles + l.begin, c->d_fac);
       break;
     case K_GEMM:
       if (l.count <= 0) break;
@@ -877,6 +887,7 @@ int chol_partition_stats(chol_t *c, double *out8) {
     if (l.kind == K_GEMM) f += l.flops;
     if (l.kind == K_PUSH) sh += (l.count > 0 && l.mask);
     for (int64_t i = l.begin; i < l.begin + l.count && l.kind == K_PANEL; i++) (c->D.pslabs[i].t >= 0 ? pt : ts) += 1.0;
+    if (l.kind == K_TRSM) ts += 2.0 * (double)l.count;  // 128-row slabs
     for (int64_t i = l.begin; i < l.begin + l.count && (l.kind == K_PUSH || l.kind == K_REDUCE); i++) {
       const RectDesc &d = c->D.rects[i];
       if (l.kind == K_PUSH) pushed += 8.0 * area(d) * bits(l.mask);
@@ -990,7 +1001,7 @@ int chol_kernel_times(chol_t *c, double *potrf_ms /* panel_ms */, double *trsm_m
       }))
     return -1;
   chol_t *r = first_rank(c);
-  if (potrf_ms) *potrf_ms = r->k_ms[K_PANEL];  // panel_kernel: diagonal blocks and the rows below them
+  if (potrf_ms) *potrf_ms = r->k_ms[K_PANEL] + r->k_ms[K_TRSM];  // panel_kernel + trsm_tile: diagonal blocks and the rows below them
   if (trsm_ms) *trsm_ms = r->k_ms[K_SYNC] + r->k_ms[K_PUSH] + r->k_ms[K_REDUCE];  // multi-GPU exchange (0 on one GPU)
   if (gemm_ms) *gemm_ms = r->k_ms[K_GEMM];
   if (gemm_flops) *gemm_flops = r->k_gemm_flops;

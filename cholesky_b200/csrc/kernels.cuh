@@ -540,6 +540,87 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(const PanelDesc *_
   }
 }
 
+// trsm_tile: the rows below a factored diagonal tile when there are MANY of them (more slabs than a wave or two of
+// CTAs): then throughput counts, not latency, and the rank-64 updates between tile steps run on the tuned grouped
+// GEMM instead of inside panel_kernel's slabs (schedule.cc decides per launch).
+// 128-row slab per CTA, one row per thread.  The slab (k-major, so a warp reads consecutive words) and
+// L^T live in shared memory; columns are solved eight at a time with eight independent FMA chains, the
+// eight multipliers of one k come as four broadcast vector loads.  Loops are deliberately not fully
+// unrolled: the straight-line version was instruction-fetch bound.
+constexpr int kSlab = 128;
+constexpr int kTrsmSmemBytes = (kNB * kNB + kNB + kNB * kSlab) * 8;
+// All 64 column loads of a slab row are in flight at once (measured: trsm time of 64^3 4.04 -> 3.50 ms against
+// eight rounds of eight).
+__global__ void __launch_bounds__(kSlab) trsm_tile(const TrsmDesc *__restrict__ descs, const TileRef *__restrict__ tiles,
+                                                   double *__restrict__ fac) {
+  extern __shared__ __align__(16) double tsm[];
+  double(*Lt)[kNB] = reinterpret_cast<double(*)[kNB]>(tsm);             // Lt[k][c] = L[c][k]
+  double *rdiag = tsm + kNB * kNB;                                       // 1 / L[c][c]
+  double(*xs)[kSlab] = reinterpret_cast<double(*)[kSlab]>(rdiag + kNB);  // xs[c][row in slab]
+  const TileRef tl = tiles[blockIdx.x];
+  const TrsmDesc d = descs[tl.prob];
+  const int slab = (int)tl.tr | ((int)tl.tc << 16);
+  const int tid = threadIdx.x, nb = d.nb, nb8 = (nb + 7) & ~7;
+  const double *__restrict__ Lg = fac + d.l_off;
+  const int row = slab * kSlab + tid;
+  const bool live = row < d.rows;
+  double *__restrict__ Bp = fac + d.b_off + (live ? row : 0);
+  {
+    double v[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; c++) v[c] = (live && c < nb) ? Bp[(size_t)c * d.ld] : 0.0;
+#pragma unroll
+    for (int c = 0; c < kNB; c++) xs[c][tid] = v[c];
+  }
+  {
+    constexpr int PER = kNB * kNB / kSlab;
+    double v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
+      v[u] = (r < nb && c < nb && r >= c) ? Lg[r + (size_t)c * d.ld] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      int i = tid + u * kSlab, r = i % kNB, c = i / kNB;
+      Lt[c][r] = v[u];
+      if (r == c) rdiag[r] = 1.0 / v[u];
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  for (int cb = 0; cb < nb8; cb += 8) {
+    double s[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = xs[cb + j][tid];
+#pragma unroll 4
+    for (int k = 0; k < cb; k++) {
+      const double xk = xs[k][tid];
+      const double2 *l2 = reinterpret_cast<const double2 *>(&Lt[k][cb]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double2 l = l2[j];
+        s[2 * j] -= xk * l.x;
+        s[2 * j + 1] -= xk * l.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int jj = 0; jj < j; jj++) s[j] -= s[jj] * Lt[cb + jj][cb + j];
+      s[j] *= rdiag[cb + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) xs[cb + j][tid] = s[j];
+  }
+  for (int c0 = 0; c0 < nb; c0 += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < nb) Bp[(size_t)(c0 + u) * d.ld] = xs[c0 + u][tid];
+  }
+}
+
+
 __global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *__restrict__ offs, int64_t nz, double *__restrict__ fac) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nz) {

@@ -114,6 +114,42 @@ struct Builder {
     pdiag.clear(), prows.clear(), pwmax = 0;
   }
 
+  // ---- rows below already factored diagonal blocks, the throughput way: per 64-column tile step one trsm_tile
+  // launch and one grouped GEMM (K = 64) that updates the rest of the block column, over all row ranges at once
+  struct RowRange {
+    int64_t base;  // panel offset
+    int ld, c0, w, rb, re;
+  };
+  std::vector<RowRange> bulk;
+  int64_t bulk_slabs() const {
+    int64_t s = 0;
+    for (const RowRange &r : bulk) s += (r.re - r.rb + 63) / 64;
+    return s;
+  }
+  void emit_bulk_rows(int level, int phase) {
+    int wmax = 0;
+    for (const RowRange &r : bulk) wmax = std::max(wmax, r.w);
+    for (int d0 = 0; d0 < wmax; d0 += 64) {
+      const int64_t b = (int64_t)D.trsm_tiles.size();
+      for (const RowRange &r : bulk) {
+        if (r.w <= d0) continue;
+        const int dw = std::min(64, r.w - d0), cd = r.c0 + d0;
+        D.trsm.push_back(TrsmDesc{r.base + cd + (int64_t)cd * r.ld, r.base + r.rb + (int64_t)cd * r.ld, r.ld, dw, r.re - r.rb, 0});
+        for (int sl = 0; sl < (r.re - r.rb + 127) / 128; sl++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(sl & 0xffff), (uint16_t)(sl >> 16)});
+      }
+      if ((int64_t)D.trsm_tiles.size() > b) push(mk(K_TRSM, level, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
+      begin_gemm(2);
+      for (const RowRange &r : bulk) {
+        const int dw = std::min(64, r.w - d0), e0 = d0 + dw;
+        if (r.w <= e0) continue;
+        add_problem(r.base + r.rb + (int64_t)(r.c0 + e0) * r.ld, r.ld, r.re - r.rb, r.w - e0, 0, r.base + r.rb + (int64_t)(r.c0 + d0) * r.ld,
+                    r.base + r.c0 + e0 + (int64_t)(r.c0 + d0) * r.ld, r.ld, r.ld, dw);
+      }
+      end_gemm(level, phase, false);
+    }
+    bulk.clear();
+  }
+
   // ---- grouped GEMM launches
   struct Pending {
     int prob;
@@ -123,7 +159,7 @@ struct Builder {
     int row_tile0 = -1, bcast_tc = 0;
   };
   std::vector<Pending> pend;
-  int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B)
+  int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = 64)
   const TopGroup *own = nullptr;  // mode 1 on a top panel: only the tile rows this rank owns
   void begin_gemm(int m) {
     pend.clear();
@@ -190,8 +226,9 @@ struct Builder {
         }
       flops += pd.flops;
     }
-    depend(0, 1);
-    push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, 0);
+    const int stream = mode == 2 ? 1 : 0;
+    if (stream == 0) depend(0, 1);
+    push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, stream);
   }
   void end_gemm(int level, int phase, bool small_ok) {
     // small fronts (bottom of the tree): one warp per 32x32 tile, operands straight from global memory
@@ -237,6 +274,8 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_SMALL_MN")) D.small_mn = atoi(e);
   if (const char *e = getenv("CHOL_SMALL_K")) D.small_k = atoi(e);
   if (const char *e = getenv("CHOL_NBO")) D.nbo = std::min(256, std::max(64, atoi(e) / 64 * 64));  // tuning knob: block-column width (single GPU)
+  if (const char *e = getenv("CHOL_FUSED_ROWS_MAX")) D.fused_rows_max = D.fused_rows_max_top = atoi(e);
+  if (const char *e = getenv("CHOL_FUSED_ROWS_MAX_TOP")) D.fused_rows_max_top = atoi(e);
   if (const char *e = getenv("CHOL_ROW_BLOCK")) D.row_block = std::min(kRowBlock, std::max(64, atoi(e) / 64 * 64));
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
@@ -367,18 +406,28 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
         const int phase = which == 0 ? PH_POTRF : which == 1 ? PH_TRSM : (PH_POTRF | PH_TRSM);
         for (int J = 0; J < nouter; J++) {
           const int c0 = J * NBO;
-          // the block column of every panel of the level: diagonal block + the rows below it, one launch
+          // the block column of every panel of the level: diagonal blocks and the rows below them
           for (int h = h0; h < h1; h++) {
             const int n = P.sz[h];
             if (n <= c0) continue;
             const int w = std::min(NBO, n - c0), c1 = c0 + w, r0 = (n + 1) / 2 * 2;
+            const int rb = which == 1 ? r0 : (c1 < n ? c1 : r0), re = which == 0 ? n : S.rows[h];
+            if (re > rb) B.bulk.push_back(Builder::RowRange{S.poff[h], S.ld[h], c0, w, rb, re});
+          }
+          const bool fused = B.bulk_slabs() <= D.fused_rows_max;
+          for (int h = h0; h < h1; h++) {
+            const int n = P.sz[h];
+            if (n <= c0) continue;
+            const int w = std::min(NBO, n - c0), c1 = c0 + w, r0 = (n + 1) / 2 * 2;
+            const int rb = which == 1 ? r0 : (c1 < n ? c1 : r0), re = which == 0 ? n : S.rows[h];
+            if (which == 1 && !fused) continue;
             const int desc = B.add_panel_desc(S.poff[h], S.ld[h], c0, w, P.start[h] + c0, which == 1 ? 1 : 0);
             if (which != 1) B.add_diag_slabs(desc);
-            if (which == 0) B.add_row_slabs(desc, c1, n);
-            else if (which == 1) B.add_row_slabs(desc, r0, S.rows[h]);
-            else B.add_row_slabs(desc, c1 < n ? c1 : r0, S.rows[h]);
+            if (fused && re > rb) B.add_row_slabs(desc, rb, re);
           }
           B.end_panel(lvl, phase);
+          if (fused) B.bulk.clear();
+          else B.emit_bulk_rows(lvl, phase);
           // right-looking update of everything to the right of block column J (K = NBO)
           B.begin_gemm(1);
           for (int h = h0; h < h1; h++) {
@@ -430,11 +479,16 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
         } else
           B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
         // own rows below: X <- X L_JJ^-T (the diagonal block is final in this rank's copy by now)
-        if (!mine.empty()) {
-          const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
-          for (auto &rg : mine) B.add_row_slabs(desc, rg.first, rg.second);
-          B.end_panel(lvl, phase);
-        }
+        for (auto &rg : mine) B.bulk.push_back(Builder::RowRange{base, ld, c0, w, rg.first, rg.second});
+        if (B.bulk_slabs() <= D.fused_rows_max_top) {
+          if (!mine.empty()) {
+            const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
+            for (auto &rg : mine) B.add_row_slabs(desc, rg.first, rg.second);
+            B.end_panel(lvl, phase);
+          }
+          B.bulk.clear();
+        } else
+          B.emit_bulk_rows(lvl, phase);
         // the group needs the pivot-block rows of this block column for its trailing updates: push them now ...
         {
           int64_t rb = (int64_t)D.rects.size();

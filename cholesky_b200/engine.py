@@ -225,7 +225,7 @@ class Cholesky:
         for i in range(int(self.L.chol_num_launches(self.h))):
             self.L.chol_get_launch(self.h, C.c_int64(i), C.byref(kind), C.byref(level), C.byref(phase),
                                    C.byref(ctas), C.byref(flops), C.byref(cfg))
-            names = ("panel_kernel", "-", "gemm_grouped", "peer_sync", "reduce_rects", "nop", "push_rects")
+            names = ("panel_kernel", "trsm_tile", "gemm_grouped", "peer_sync", "reduce_rects", "nop", "push_rects")
             out.append(dict(kind=names[kind.value], level=level.value, phase=phase.value, ctas=ctas.value,
                             flops=flops.value, cfg=cfg.value & 15, stream=(cfg.value >> 4) & 15, width=cfg.value >> 8))
         return out

@@ -118,6 +118,14 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
           }
         }
         break;
+      case K_TRSM:
+        for (int64_t i = l.begin; i < l.begin + l.count; i++) {
+          const TileRef &t = k.D.trsm_tiles[i];
+          const TrsmDesc &d = k.D.trsm[t.prob];
+          const int slab = (int)t.tr | ((int)t.tc << 16);
+          trsm(fac + d.l_off, fac + d.b_off, d.ld, d.nb, slab * 128, std::min(d.rows, (slab + 1) * 128));
+        }
+        break;
       case K_GEMM: {
         const int bm = l.cfg == 3 ? 32 : 64;
         gemm_flops += l.flops;

@@ -105,6 +105,19 @@ def test_large_front_blocking_paths(tmp_path):
     assert ch.residual(k=4) <= 1e-12
 
 
+@pytest.mark.parametrize("fused_rows_max", ["0", "1000000"])
+def test_both_paths_for_the_rows_below_a_diagonal_block(monkeypatch, fused_rows_max):
+    """the rows below the diagonal blocks of a launch go through panel_kernel's slabs when they are few and through
+    trsm_tile + grouped GEMM launches when they are many (schedule.cc); force each path for every launch"""
+    monkeypatch.setenv("CHOL_FUSED_ROWS_MAX", fused_rows_max)
+    ch = Cholesky().generate(41, 40, 39, 7, 3).analyze()
+    ch.factor()
+    assert ch.residual(k=4) <= 1e-12
+    b = np.random.default_rng(1).integers(1, 11, size=ch.n).astype(np.float64)
+    x = ch.solve(b)
+    assert np.linalg.norm(b - ch.matvec(x)) <= 1e-12 * np.linalg.norm(b)
+
+
 def test_idempotent_and_deterministic(golden):
     g = golden["lapl_3375x3375"]
     ch = Cholesky().load(g.mtx, g.ord, g.clust).analyze()

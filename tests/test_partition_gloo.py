@@ -69,16 +69,18 @@ def test_partition_covers_single_rank_schedule(world):
 
     sub = lambda l: l["level"] >= depth      # noqa: E731
     top = lambda l: l["level"] < depth       # noqa: E731
-    for kind, key in (("gemm_grouped", "flops"), ("panel_kernel", "ctas")):
-        # subtree levels: split with no overlap
-        assert sum(total(r["launches"], kind, key, sub) for r in ranks) == pytest.approx(
-            total(single["launches"], kind, key, sub), rel=1e-12)
+    # subtree levels: the Schur updates are split with no overlap (the in-panel work depends on how many rows a launch
+    # holds -- few: panel_kernel slabs, many: trsm_tile + GEMM -- so it is compared through the tile counts below)
+    schur = lambda l: l["level"] >= depth and l["phase"] == 4      # noqa: E731
+    assert sum(total(r["launches"], "gemm_grouped", "flops", schur) for r in ranks) == pytest.approx(
+        total(single["launches"], "gemm_grouped", "flops", schur), rel=1e-12)
     # top levels: every pivot tile is factored by exactly one rank (the owner of its diagonal block) ...
     assert sum(r["stats"]["diag_tiles"] for r in ranks) == single["stats"]["diag_tiles"]
     # ... and the executed flops of the top levels are those of the single-rank schedule, dealt out with no overlap
     # (a few masked rows at odd ownership boundaries and the per-tile accounting of split launches aside)
-    split_flops = sum(total(r["launches"], "gemm_grouped", "flops", top) for r in ranks)
-    assert split_flops == pytest.approx(total(single["launches"], "gemm_grouped", "flops", top), rel=3e-2)
+    topschur = lambda l: top(l) and l["phase"] == 4      # noqa: E731
+    split_flops = sum(total(r["launches"], "gemm_grouped", "flops", topschur) for r in ranks)
+    assert split_flops == pytest.approx(total(single["launches"], "gemm_grouped", "flops", topschur), rel=3e-2)
     per_rank = [total(r["launches"], "gemm_grouped", "flops", top) for r in ranks]
     assert max(per_rank) <= 1.35 * min(per_rank)          # dealt evenly (small grid: coarse blocks)
     for r in ranks:

@@ -46,6 +46,18 @@ def test_simulated_partitioned_factor_matches_oracle(monkeypatch, world, grid, r
             assert st["push_rects"] > 0 and st["reduces"] > 0
 
 
+@pytest.mark.parametrize("world", [1, 4])
+def test_simulated_schedule_with_the_throughput_path_for_the_rows(monkeypatch, world):
+    """CHOL_FUSED_ROWS_MAX=0: the rows below every diagonal block go through trsm_tile + grouped GEMM launches per
+    64-column tile step instead of panel_kernel's slabs (the path large fronts take by default)"""
+    monkeypatch.setenv("CHOL_ROW_BLOCK", "128")
+    monkeypatch.setenv("CHOL_FUSED_ROWS_MAX", "0")
+    grid = (16, 16, 16, 7, 5)
+    L, copy_diff, _ = sim.factor(grid, world, 7)
+    ok, worst = entrywise_ok(L, oracle_factor(grid))
+    assert ok and copy_diff == 0.0, worst
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_simulated_schedule_without_lookahead(monkeypatch, world):
     """CHOL_LOOKAHEAD=0 puts every launch of a rank on one stream in list order: the order of the instrumented
