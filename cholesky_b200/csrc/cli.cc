@@ -1,6 +1,9 @@
 // `cholesky` command line: the reference's flags (mmat.rg:1072-1093) over the C ABI.
 //   -i matrix.mtx -s separators.txt -c clusters.txt [-b rhs.mtx -o solution] [-m factor.mtx]
-//   [-p permuted.mtx] [-d debug_dir] [--iterations N] [--gpu D] [--binary-factor factor.bin]
+//   [-p permuted.mtx] [-d debug_dir] [--iterations N] [--gpu D | --gpus N] [--binary-factor factor.bin]
+// --gpus N (2, 4 or 8) runs the factorization and the solve subtree-partitioned over CUDA devices 0 .. N-1 from this
+// one process (the counterpart of the reference's -ll:gpu processor selection), --devices d0,d1,.. over an explicit
+// list (a device may repeat: several ranks then share it); --gpu D picks one device.
 //   cholesky --convert factor.bin factor.mtx      (binary dump -> the reference's text format, no GPU)
 // Progress lines follow the reference's stdout (mmat.rg:1095-1121, 1228, 1357).
 #include <cstdio>
@@ -12,7 +15,8 @@
 
 int main(int argc, char **argv) {
   const char *mat = "", *sep = "", *clu = "", *bfile = "", *sol = "", *fac = "", *perm = "", *dbg = "";
-  int iterations = 1, gpu = 0;
+  int iterations = 1, gpu = 0, gpus = 1;
+  const char *devlist = "";
   const char *binfac = "";
   if (argc == 4 && !strcmp(argv[1], "--convert")) {
     int rc = chol_factor_binary_to_mtx(argv[2], argv[3], 0);
@@ -30,11 +34,27 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "-d")) dbg = argv[i + 1];  // debug_path, debug = true (mmat.rg:1086-1090)
     else if (!strcmp(argv[i], "--iterations")) iterations = atoi(argv[i + 1]);
     else if (!strcmp(argv[i], "--gpu")) gpu = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "--gpus")) gpus = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "--devices")) devlist = argv[i + 1];
     else if (!strcmp(argv[i], "--binary-factor")) binfac = argv[i + 1];
   }
   printf("Iterations: %d\n", iterations);
   chol_t *c = nullptr;
-  if (chol_create(&gpu, 1, &c)) return 1;
+  std::vector<int> devices;
+  for (int d = 0; d < gpus; d++) devices.push_back(gpus > 1 ? d : gpu);
+  if (*devlist) {
+    devices.clear();
+    for (const char *q = devlist; *q;) {
+      devices.push_back(atoi(q));
+      while (*q && *q != ',') q++;
+      if (*q == ',') q++;
+    }
+  }
+  if (chol_create(devices.data(), (int)devices.size(), &c)) {
+    printf("the factorization runs on 1, 2, 4 or 8 GPUs\n");
+    return 1;
+  }
+  if (devices.size() > 1) printf("GPUs: %d\n", (int)devices.size());
   if (chol_load(c, mat, sep, clu)) {
     printf("%s\n", chol_last_error(c));
     return 1;

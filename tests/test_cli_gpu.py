@@ -46,6 +46,24 @@ def test_matrices(case, golden, tmp_path):
         assert line in text, line
 
 
+def test_devices_flag_runs_the_partitioned_path(golden, tmp_path):
+    """--devices 0,0: two ranks driven from the one process (here sharing cuda:0), same outputs as the single-GPU run"""
+    import scipy.io
+    g = golden["lapl_3375x3375"]
+    out = tmp_path / "output"
+    out.mkdir()
+    args = [CLI, "-i", g.mtx, "-s", g.ord, "-c", g.clust, "-b", g.b, "-o", str(out / "solution.mtx"), "-m", str(out / "factored.mtx"),
+            "--devices", "0,0"]
+    env = dict(os.environ, CHOL_ROW_BLOCK="64", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    with open(out / "stdout", "w") as f:
+        assert subprocess.call(args, stdout=f, env=env) == 0, open(out / "stdout").read()
+    assert "GPUs: 2" in open(out / "stdout").read()
+    L = np.tril(np.asarray(scipy.io.mmread(str(out / "factored.mtx")).todense()))
+    assert np.allclose(g.L_dense(), L, rtol=1e-04, atol=1e-04)
+    assert np.allclose(g.x, np.genfromtxt(str(out / "solution.mtx")).reshape(-1), rtol=1e-04, atol=1e-04)
+    assert subprocess.call([CLI, "-i", g.mtx, "-s", g.ord, "-c", g.clust, "--gpus", "3"], stdout=subprocess.DEVNULL) != 0
+
+
 def test_iterations_flag(golden, tmp_path):
     g = golden["lapl_400x400"]
     out = str(tmp_path / "stdout")
