@@ -107,8 +107,8 @@ def describe(name, grid):
 def host_can_run_full(workload):
     """the oracle keeps the whole factor in host memory (the reference's filled clusters, 128^3: 25.5 GiB) and needs
     about a minute of multi-threaded BLAS for 128^3 on 16 cores"""
-    if os.environ.get("CHOL_REF_SAMPLE") == "1":
-        return False
+    if os.environ.get("CHOL_REF_SAMPLE") in ("0", "1"):    # 1: always the bounded sample, 0: always the full workload
+        return os.environ["CHOL_REF_SAMPLE"] == "0"
     need_gb = {"lapl3d_7pt_128": 48, "lapl3d_27pt_96": 24}.get(workload, 8)
     try:
         avail = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0] / 2**20

@@ -337,22 +337,44 @@ constexpr long long kSpinLimit = 6000000000LL;  // ~3 s at 2 GHz: a wait gives u
 inline size_t panel_smem_bytes(int wmax) { return ((size_t)((wmax + kNB - 1) / kNB * kNB) * kLdx + (size_t)kNB * kLdx + kNB) * sizeof(double); }
 
 // Cholesky of the 64 x 64 tile T (entry (i, c) at T[c * kLdx + i]) in shared memory, right-looking in panels of
-// eight columns.  The 64 dependent column steps are what a tile costs, so they are kept as short as the hardware
-// allows (B200, tools/lat_bench.cu: rsqrt(double) 74 cycles, dependent DFMA 8, a publish through shared memory and
-// a named barrier 56): ONE warp holds the panel in registers, two rows per lane, and does its eight steps with
-// shuffles only -- pivot broadcast, rsqrt, scale, rank-1 update of the remaining panel columns -- then all eight
-// warps apply the rank-8 update to the trailing part.  Columns >= dw are an identity block (steps skipped).
+// eight columns, with look-ahead inside the tile.  The 64 dependent column steps are what a tile costs, so the
+// warp that does them never waits for anything else:
+//   warp 0       holds the current panel in registers (two rows per lane); a column step is a shuffle of the
+//                pivot and of the panel's raw pivot-row entries, rsqrt, and the rank-1 update of the remaining
+//                panel columns (B200, tools/lat_bench.cu: rsqrt(double) 74 cycles, dependent DFMA 8).  After its
+//                eight steps it stores the panel, applies it to the NEXT panel's columns itself (registers) and
+//                goes on;
+//   warps 1 - 7  apply every finished panel to the columns two panels and more to the right, one panel behind
+//                warp 0 (named barriers A_p: panel p is in shared memory, B_p: its trailing update is done).
+// Measured per tile in tools/potrf_bench.cu.  Columns >= dw are an identity block.  Ends with a block barrier.
+// named barriers 1 .. 4 over the whole CTA (immediate ids: a register id would make ptxas reserve all sixteen
+// barriers of the SM for one CTA); odd selects the second of a pair
+template <int ID>
+__device__ __forceinline__ void bar_sync_pair(bool odd) {
+  if (odd) asm volatile("bar.sync %0, %1;\n" ::"n"(ID + 1), "n"(kPanelThreads) : "memory");
+  else asm volatile("bar.sync %0, %1;\n" ::"n"(ID), "n"(kPanelThreads) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_arrive_pair(bool odd) {
+  if (odd) asm volatile("bar.arrive %0, %1;\n" ::"n"(ID + 1), "n"(kPanelThreads) : "memory");
+  else asm volatile("bar.arrive %0, %1;\n" ::"n"(ID), "n"(kPanelThreads) : "memory");
+}
 __device__ __forceinline__ void potrf_smem(double *__restrict__ T, int dw, int col0, int *__restrict__ info) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int k0 = 0; k0 < dw; k0 += 8) {
-    if (warp == 0) {
-      double x0[8], x1[8];  // rows lane and lane + 32 of the panel
+  const int np = (dw + 7) >> 3;  // panels; panel p has trailing columns (two panels and more to the right) iff p + 2 < np
+  if (warp == 0) {
+    double x0[8], x1[8];  // rows lane and lane + 32 of the current panel
 #pragma unroll
-      for (int j = 0; j < 8; j++) x0[j] = T[(k0 + j) * kLdx + lane], x1[j] = T[(k0 + j) * kLdx + lane + 32];
+    for (int j = 0; j < 8; j++) x0[j] = T[j * kLdx + lane], x1[j] = T[j * kLdx + lane + 32];
+    for (int p = 0; p < np; p++) {
+      const int k0 = 8 * p;
       const bool hi = k0 >= 32;  // the panel's own rows k0 .. k0 + 7 sit in x1 (of lanes k0 - 32 ..) or in x0
 #pragma unroll
       for (int kk = 0; kk < 8; kk++) {
         double dk = __shfl_sync(0xffffffffu, hi ? x1[kk] : x0[kk], (k0 + kk) & 31);
+        double raw[8];  // column kk of the panel's own rows below the pivot, before scaling: independent of the rsqrt
+#pragma unroll
+        for (int j = kk + 1; j < 8; j++) raw[j] = __shfl_sync(0xffffffffu, hi ? x1[kk] : x0[kk], (k0 + j) & 31);
         if (!(dk > 0.0)) {
           if (lane == 0) atomicMin(info, col0 + k0 + kk + 1);  // 1-based permuted column of the first bad pivot
           dk = 1.0;
@@ -361,7 +383,7 @@ __device__ __forceinline__ void potrf_smem(double *__restrict__ T, int dw, int c
         x0[kk] *= r, x1[kk] *= r;  // the pivot row's own entry becomes dk / sqrt(dk); rows above it hold garbage that is never stored
 #pragma unroll
         for (int j = kk + 1; j < 8; j++) {
-          const double ljk = __shfl_sync(0xffffffffu, hi ? x1[kk] : x0[kk], (k0 + j) & 31);
+          const double ljk = raw[j] * r;
           x0[j] = fma(-x0[kk], ljk, x0[j]);
           x1[j] = fma(-x1[kk], ljk, x1[j]);
         }
@@ -371,27 +393,49 @@ __device__ __forceinline__ void potrf_smem(double *__restrict__ T, int dw, int c
         if (lane >= k0 + j) T[(k0 + j) * kLdx + lane] = x0[j];
         if (lane + 32 >= k0 + j) T[(k0 + j) * kLdx + lane + 32] = x1[j];
       }
-    }
-    __syncthreads();
-    const int e0 = k0 + 8;
-    if (e0 < dw) {  // T(i, j) -= sum_k T(i, k) T(j, k) over the panel just factored, i >= j >= e0; thread = row i, every fourth column j
-      const int i = tid & (kNB - 1);
-      double ri[8];
+      __syncwarp();
+      if (p + 2 < np) bar_arrive_pair<1>(p & 1);  // A_p
+      if (p + 1 < np) {
+        if (p >= 1) bar_sync_pair<3>((p - 1) & 1);  // B_{p-1}: the next panel's columns have every update but this panel's
+        double y0[8], y1[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) ri[k] = T[(k0 + k) * kLdx + i];
-      for (int j = e0 + (tid >> 6); j < dw; j += kPanelThreads / kNB) {
-        if (j > i) continue;
-        double s0 = 0.0, s1 = 0.0;
+        for (int j = 0; j < 8; j++) y0[j] = T[(k0 + 8 + j) * kLdx + lane], y1[j] = T[(k0 + 8 + j) * kLdx + lane + 32];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          s0 = fma(ri[k], T[(k0 + k) * kLdx + j], s0);
-          s1 = fma(ri[k + 1], T[(k0 + k + 1) * kLdx + j], s1);
+        for (int k = 0; k < 8; k++) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const double ljk = T[(k0 + k) * kLdx + k0 + 8 + j];  // entry (row k0 + 8 + j, column k0 + k) of the panel just stored
+            y0[j] = fma(-x0[k], ljk, y0[j]);
+            y1[j] = fma(-x1[k], ljk, y1[j]);
+          }
         }
-        T[j * kLdx + i] -= s0 + s1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) x0[j] = y0[j], x1[j] = y1[j];
       }
     }
-    __syncthreads();
+  } else {
+    for (int p = 0; p + 2 < np; p++) {
+      const int k0 = 8 * p, e0 = k0 + 16;
+      bar_sync_pair<1>(p & 1);  // A_p
+      double r0[8], r1[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) r0[k] = T[(k0 + k) * kLdx + lane], r1[k] = T[(k0 + k) * kLdx + lane + 32];
+      for (int j = e0 + warp - 1; j < 8 * np; j += 7) {  // T(i, j) -= sum_k T(i, k) T(j, k), i >= j
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double ljk = T[(k0 + k) * kLdx + j];
+          s0 = fma(r0[k], ljk, s0);
+          s1 = fma(r1[k], ljk, s1);
+        }
+        if (lane >= j) T[j * kLdx + lane] -= s0;
+        if (lane + 32 >= j) T[j * kLdx + lane + 32] -= s1;
+      }
+      __syncwarp();
+      bar_arrive_pair<3>(p & 1);  // B_p
+    }
   }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kPanelThreads) panel_kernel(const PanelDesc *__restrict__ descs, const PanelSlab *__restrict__ slabs,

@@ -44,6 +44,12 @@ namespace chb {
 namespace {
 
 constexpr int kNoTri = 1 << 30;
+// Order of the CTAs of one GEMM problem: groups of 16 tile rows, and inside a group column by column.  The CTAs in
+// flight at any time (three per SM) then share 16 row tiles of the A operand and a couple of dozen column tiles of
+// the B operand, which fit the 126 MB L2 even at K = 8 128, instead of streaming the whole A operand once per
+// tile column.  ncu on the level-3 Schur update of 128^3 (K = 4 009, 123 922 tiles, 136 ms at 96.5 % DMMA pipe):
+// DRAM reads 148 GB with plain column-major order against ~10 GB of distinct operands and destinations.
+constexpr int kTileRowGroup = 16;
 
 struct Builder {
   const Problem &P;
@@ -194,13 +200,14 @@ struct Builder {
       for (const Pending &pd : list) {
         const GemmProblem &g = D.probs[pd.prob];
         int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
-        for (int tc = 0; tc < tc_n; tc++)
-          for (int tr = 0; tr < tr_n; tr++) {
-            if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;
-            all_tiles += 1;
-            if (own && own->owner((pd.row_tile0 + tr) * bm / own->rb) != D.rank) continue;
-            (tc < pd.bcast_tc ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
-          }
+        for (int tb = 0; tb < tr_n; tb += kTileRowGroup)  // L2-friendly order, see kTileRowGroup
+          for (int tc = 0; tc < tc_n; tc++)
+            for (int tr = tb; tr < std::min(tr_n, tb + kTileRowGroup); tr++) {
+              if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;
+              all_tiles += 1;
+              if (own && own->owner((pd.row_tile0 + tr) * bm / own->rb) != D.rank) continue;
+              (tc < pd.bcast_tc ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+            }
         flops += pd.flops;
       }
       const double per_tile = flops / std::max(1.0, all_tiles);
@@ -219,11 +226,12 @@ struct Builder {
     for (const Pending &pd : list) {
       const GemmProblem &g = D.probs[pd.prob];
       int tr_n = (g.M + bm - 1) / bm, tc_n = (g.N + bn - 1) / bn;
-      for (int tc = 0; tc < tc_n; tc++)
-        for (int tr = 0; tr < tr_n; tr++) {
-          if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
-          D.tiles.push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
-        }
+      for (int tb = 0; tb < tr_n; tb += kTileRowGroup)
+        for (int tc = 0; tc < tc_n; tc++)
+          for (int tr = tb; tr < std::min(tr_n, tb + kTileRowGroup); tr++) {
+            if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;  // wholly above the diagonal
+            D.tiles.push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+          }
       flops += pd.flops;
     }
     const int stream = mode == 2 ? 1 : 0;

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from bench import WORKLOADS  # noqa: E402
 from cholesky_b200 import Cholesky  # noqa: E402
 
-OURS = ("gemm_grouped", "gemm_small_warp", "panel_kernel")  # kernels of the launch table
+OURS = ("gemm_grouped", "gemm_small_warp", "panel_kernel", "trsm_tile")  # kernels of the launch table
 PHASE = {1: "fused_dpotrf", 2: "fused_dtrsm", 3: "fused_dpotrf+dtrsm", 4: "fused_dsyrk/dgemm"}
 
 
@@ -29,7 +29,7 @@ def main():
     other = [(r[ki], float(r[vi].replace(",", "")) * scale[r[ui]]) for r in rows[1:]
              if not any(k in r[ki] for k in OURS)]
     ch = Cholesky().generate(*WORKLOADS[workload]).analyze()
-    ls = [l for l in ch.launches() if l["kind"] in ("gemm_grouped", "panel_kernel")]
+    ls = [l for l in ch.launches() if l["kind"] in ("gemm_grouped", "panel_kernel", "trsm_tile")]
     n = min(len(ls), len(ours))
     agg = collections.OrderedDict()
     tot = 0.0
