@@ -1337,7 +1337,10 @@ struct SolveDev {
   SolveSchedule V;
   SolveTile *tiles = nullptr;
   SolveGemv *gemv = nullptr;
-  TileRef *gemv_tiles = nullptr, *pull_tiles = nullptr, *gather_tiles = nullptr;
+  TileRef *gemv_tiles = nullptr, *gather_tiles = nullptr;
+  PullTile *pull_tiles = nullptr;
+  PullSum *pull_sums = nullptr;
+  double *scratch = nullptr;
   PullDest *pull = nullptr;
   PullContrib *pull_contrib = nullptr;
   GatherDesc *gather = nullptr;
@@ -1349,6 +1352,7 @@ static void free_solve(chol_t *c) {
   if (!v) return;
   cudaFree(v->tiles), cudaFree(v->gemv), cudaFree(v->gemv_tiles), cudaFree(v->pull_tiles), cudaFree(v->gather_tiles);
   cudaFree(v->pull), cudaFree(v->pull_contrib), cudaFree(v->gather), cudaFree(v->rowmap), cudaFree(v->perm), cudaFree(v->x), cudaFree(v->io);
+  cudaFree(v->pull_sums), cudaFree(v->scratch);
   delete v;
   c->solve = nullptr;
 }
@@ -1360,10 +1364,12 @@ static int ensure_solve(chol_t *c) {
   if (upload(c, &v->tiles, v->V.tiles) || upload(c, &v->gemv, v->V.gemv) || upload(c, &v->gemv_tiles, v->V.gemv_tiles) ||
       upload(c, &v->pull, v->V.pull) || upload(c, &v->pull_contrib, v->V.pull_contrib) || upload(c, &v->pull_tiles, v->V.pull_tiles) ||
       upload(c, &v->gather, v->V.gather) || upload(c, &v->gather_tiles, v->V.gather_tiles) || upload(c, &v->rowmap, v->V.rowmap) ||
+      upload(c, &v->pull_sums, v->V.pull_sums) ||
       upload(c, &v->perm, c->P.perm))
     return -100;
   CK(cudaMalloc((void **)&v->x, std::max(1, c->P.n) * sizeof(double)));
   CK(cudaMalloc((void **)&v->io, std::max(1, c->P.n) * sizeof(double)));
+  CK(cudaMalloc((void **)&v->scratch, std::max<size_t>(1, (size_t)v->V.pull_slots * kSolveSlab) * sizeof(double)));
   v->ready = true;
   return 0;
 }
@@ -1374,15 +1380,26 @@ extern "C" {
 static void run_solve_launches(chol_t *c, size_t from, size_t to) {
   SolveDev *v = c->solve;
   cudaStream_t st = c->stream;
+  // CHOL_SOLVE_TIMES=1: device time by kernel class and tree level of this sweep on stderr (a measurement aid)
+  static const bool timing = getenv("CHOL_SOLVE_TIMES") && atoi(getenv("CHOL_SOLVE_TIMES"));
+  std::vector<cudaEvent_t> ev;
   for (size_t i = from; i < to; i++) {
     const SolveLaunch &l = v->V.launches[i];
     const unsigned g = (unsigned)l.count;
+    if (timing) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, st);
+      ev.push_back(e);
+    }
     switch (l.kind) {
       case SK_TILE_F:
-        solve_tile<false><<<g, kSolveNB, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        if (l.width <= kSolveNB) solve_tile<false><<<g, kSolveTileThreads, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        else solve_block<false><<<g, kSolveBlockThreads, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
         break;
       case SK_TILE_B:
-        solve_tile<true><<<g, kSolveNB, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        if (l.width <= kSolveNB) solve_tile<true><<<g, kSolveTileThreads, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
+        else solve_block<true><<<g, kSolveBlockThreads, 0, st>>>(v->tiles + l.begin, c->d_fac, v->x);
         break;
       case SK_GEMV_F:
         solve_gemv_fwd<<<g, kSolveSlab, 0, st>>>(v->gemv, v->gemv_tiles + l.begin, c->d_fac, v->x);
@@ -1391,7 +1408,10 @@ static void run_solve_launches(chol_t *c, size_t from, size_t to) {
         solve_gemv_bwd<<<g, kSolveColG * 32, 0, st>>>(v->gemv, v->gemv_tiles + l.begin, c->d_fac, v->x);
         break;
       case SK_PULL:
-        solve_pull<<<g, kSolveSlab, 0, st>>>(v->pull, v->pull_contrib, v->pull_tiles + l.begin, c->d_fac, v->x);
+        solve_pull<<<g, kSolveSlab, 0, st>>>(v->pull, v->pull_contrib, v->pull_tiles + l.begin, c->d_fac, v->x, v->scratch);
+        break;
+      case SK_PULL_SUM:
+        solve_pull_sum<<<g, kSolveSlab, 0, st>>>(v->pull_sums + l.begin, v->scratch, v->x);
         break;
       case SK_GATHER:
         solve_gather<<<g, kSolveColG * 32, 0, st>>>(v->gather, v->gather_tiles + l.begin, v->rowmap, c->d_fac, v->x);
@@ -1399,6 +1419,31 @@ static void run_solve_launches(chol_t *c, size_t from, size_t to) {
       case SK_EXCHANGE:
         break;
     }
+  }
+  if (timing && !ev.empty()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    cudaStreamSynchronize(st);
+    double by[8][32] = {};
+    int cnt[8] = {};
+    for (size_t i = from; i < to; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - from], ev[i - from + 1]);
+      const SolveLaunch &l = v->V.launches[i];
+      by[l.kind][std::min(l.level, 31)] += ms, cnt[l.kind]++;
+    }
+    const char *names[8] = {"tile_fwd", "gemv_fwd", "pull", "gather", "tile_bwd", "gemv_bwd", "exchange", "pull_sum"};
+    for (int k = 0; k < 8; k++) {
+      double tot = 0;
+      for (int l = 0; l < 32; l++) tot += by[k][l];
+      if (!cnt[k]) continue;
+      fprintf(stderr, "solve %-9s %5d launches %8.3f ms; by level:", names[k], cnt[k], tot);
+      for (int l = 0; l < c->P.levels; l++) fprintf(stderr, " %.2f", by[k][l]);
+      fprintf(stderr, "\n");
+    }
+    for (cudaEvent_t x : ev) cudaEventDestroy(x);
   }
 }
 static size_t solve_exchange_index(const SolveSchedule &V) {
@@ -1515,6 +1560,7 @@ int chol_solve_stats(chol_t *c, double *out12) {
   for (int i = 0; i < 12; i++) out12[i] = 0;
   for (const SolveLaunch &l : V.launches) {
     if (l.kind == SK_EXCHANGE) continue;
+    if (l.kind == SK_PULL_SUM) continue;
     const int slot = l.kind == SK_TILE_F ? 0 : l.kind == SK_GEMV_F ? 1 : l.kind == SK_PULL ? 2 : l.kind == SK_GATHER ? 3 : l.kind == SK_TILE_B ? 4 : 5;
     const bool top = c->world > 1 && l.level < V.depth;
     out12[slot + (top ? 6 : 0)] += (double)l.count;

@@ -28,15 +28,27 @@ struct PullContrib {
   int64_t p_off;
   int ld, K, x0, pad;
 };
+// One CTA of a pull: 128 rows of a destination, columns [kbeg, kend) of the destination's contributors laid end to
+// end.  Destinations with many contributor columns (the top of the tree: a few thousand rows against K of several
+// thousand) are split over CTAs so that the sweep has enough loads in flight; a split tile parks its partial sums
+// in scratch slot `slot` and a second launch adds the slots up in order (deterministic), slot < 0: the tile holds
+// all columns and subtracts from x directly.
+struct PullTile {
+  int dest, slab, kbeg, kend, slot;
+};
+struct PullSum {  // x[y0 + r] -= sum_{p < nparts} scratch[(slot0 + p) * 128 + r], r < rows
+  int y0, rows, slot0, nparts;
+};
 struct GatherDesc {  // x[x0 + c] -= sum_{r < nrows} P[r, c] x[rowmap[map_off + r]]
   int64_t p_off, map_off;
   int ld, nrows, n, x0;
 };
-enum SolveKind { SK_TILE_F = 0, SK_GEMV_F = 1, SK_PULL = 2, SK_GATHER = 3, SK_TILE_B = 4, SK_GEMV_B = 5, SK_EXCHANGE = 6 };
+enum SolveKind { SK_TILE_F = 0, SK_GEMV_F = 1, SK_PULL = 2, SK_GATHER = 3, SK_TILE_B = 4, SK_GEMV_B = 5, SK_EXCHANGE = 6, SK_PULL_SUM = 7 };
 struct SolveLaunch {
   int kind;
   int64_t begin, count;  // range in tiles_f / gemv_tiles / pull_tiles / gather_tiles / tiles_b
   int level;             // tree level the launch works on
+  int width;             // SK_TILE_*: the widest diagonal block of the launch (<= 64: the light tile kernel)
 };
 struct SolveSchedule {
   std::vector<SolveTile> tiles;       // indexed directly by SK_TILE_* launches
@@ -44,7 +56,9 @@ struct SolveSchedule {
   std::vector<TileRef> gemv_tiles;    // (gemv desc, slab)
   std::vector<PullDest> pull;
   std::vector<PullContrib> pull_contrib;
-  std::vector<TileRef> pull_tiles;    // (dest, slab)
+  std::vector<PullTile> pull_tiles;   // (dest, slab, column range)
+  std::vector<PullSum> pull_sums;
+  int64_t pull_slots = 0;             // scratch slots (128 doubles each) the largest pull launch needs
   std::vector<GatherDesc> gather;
   std::vector<TileRef> gather_tiles;  // (gather desc, column group)
   std::vector<int> rowmap;            // global permuted row of every stored off-diagonal panel row (-1: padding)
