@@ -137,7 +137,7 @@ struct Launch {
   double flops;          // executed flops (for per-kernel accounting), GEMM only
   int cfg;               // GEMM: 0 = 64x64 CTA tiles on shared-memory operand rings, 3 = one warp per 32x32 tile;
                          // K_PANEL: the widest block column of the launch (sizes its shared memory)
-  int stream;            // 0 = update stream, 1 = chain stream (look-ahead), 2 = background pushes
+  int stream;            // 0 = update stream, 1 = chain stream (look-ahead), 2 = background pushes, 3 = rows stream (top panels)
   int wait_ev, rec_ev;   // event to wait for before / to record after the launch (-1: none)
   // multi-GPU (K_PUSH / K_SYNC / K_REDUCE): `mask` = ranks the rectangles are pushed to / reduced from;
   // after a push (or as the first half of a sync) flag word (slot, this rank) of every rank in `sig_mask`
@@ -179,6 +179,7 @@ struct Schedule {
   bool lookahead = true;      // chain kernels on a second stream, overlapping the trailing updates (CHOL_LOOKAHEAD=0: off)
   int num_events = 0;         // cross-stream events the launch list refers to
   int64_t top_doubles = 0;    // leading part of the factor buffer that holds the top panels (one copy per rank)
+  bool deep = true;           // top panels: the chain of the diagonal blocks runs ahead of the group's row exchange (CHOL_DEEP=0: off)
   int row_block = kRowBlock;  // rows of a top panel are dealt to its group in blocks of this many (= block-column width there)
 };
 

@@ -29,7 +29,7 @@
 using namespace chb;
 
 constexpr int kMaxDevices = 16;
-constexpr int kStreams = 3;  // update stream, chain stream (look-ahead), background pushes
+constexpr int kStreams = 4;  // update stream, chain stream (look-ahead), background pushes, rows stream (top panels of a partition)
 
 struct SolveDev;
 struct ResDev;
@@ -46,7 +46,7 @@ struct chol {
   int device = 0;
   Schedule D;
   bool loaded = false, analyzed = false, device_ready = false, assembled = false, factored = false;
-  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t &stream = streams[0];
   cudaStream_t cur = nullptr;  // stream of the launch being issued
   double *d_fac = nullptr;
@@ -69,7 +69,7 @@ struct chol {
   std::vector<double> h_fac;  // host copy of the factor, fetched lazily
   bool h_fac_valid = false;
   std::vector<cudaEvent_t> evs;  // cross-stream events of the launch list
-  cudaEvent_t ev_fork = nullptr, ev_join[kStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kStreams] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};  // timing events of a step
   std::vector<cudaEvent_t> kev;                      // two per launch, for the instrumented pass
   double k_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -400,6 +400,7 @@ static int rank_device(chol_t *c) {  // one rank: streams, buffers, descriptor a
     CK(cudaStreamCreateWithPriority(&c->streams[0], cudaStreamNonBlocking, std::min(lo, hi + 1)));
     CK(cudaStreamCreateWithPriority(&c->streams[1], cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&c->streams[2], cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&c->streams[3], cudaStreamNonBlocking, hi));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < kStreams; i++) CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));

@@ -58,8 +58,9 @@ struct Builder {
   Builder(const Problem &p, const Symbolic &s, Schedule &d) : P(p), S(s), D(d) {}
 
   // ---- launches, streams and events
-  int last[3] = {-1, -1, -1};   // index of the last launch pushed on each stream
-  int pendw[3] = {-1, -1, -1};  // event the next launch of the stream has to wait for
+  int last[4] = {-1, -1, -1, -1};   // index of the last launch pushed on each stream
+  int pendw[4] = {-1, -1, -1, -1};  // event the next launch of the stream has to wait for
+  int chain = 1;                    // stream of the panel launches and chain GEMMs being emitted (1, or 3: the rows stream)
   static Launch mk(int kind, int level, int phase, int64_t begin = 0, int64_t count = 0, double flops = 0, int cfg = 0) {
     Launch l;
     l.kind = kind, l.level = level, l.phase = phase, l.begin = begin, l.count = count, l.flops = flops, l.cfg = cfg;
@@ -116,7 +117,7 @@ struct Builder {
     const int64_t b = (int64_t)D.pslabs.size();
     D.pslabs.insert(D.pslabs.end(), pdiag.begin(), pdiag.end());
     D.pslabs.insert(D.pslabs.end(), prows.begin(), prows.end());
-    if ((int64_t)D.pslabs.size() > b) push(mk(K_PANEL, level, phase, b, (int64_t)D.pslabs.size() - b, 0, pwmax), 1);
+    if ((int64_t)D.pslabs.size() > b) push(mk(K_PANEL, level, phase, b, (int64_t)D.pslabs.size() - b, 0, pwmax), chain);
     pdiag.clear(), prows.clear(), pwmax = 0;
   }
 
@@ -143,7 +144,7 @@ struct Builder {
         D.trsm.push_back(TrsmDesc{r.base + cd + (int64_t)cd * r.ld, r.base + r.rb + (int64_t)cd * r.ld, r.ld, dw, r.re - r.rb, 0});
         for (int sl = 0; sl < (r.re - r.rb + 127) / 128; sl++) D.trsm_tiles.push_back(TileRef{(int)D.trsm.size() - 1, (uint16_t)(sl & 0xffff), (uint16_t)(sl >> 16)});
       }
-      if ((int64_t)D.trsm_tiles.size() > b) push(mk(K_TRSM, level, phase, b, (int64_t)D.trsm_tiles.size() - b), 1);
+      if ((int64_t)D.trsm_tiles.size() > b) push(mk(K_TRSM, level, phase, b, (int64_t)D.trsm_tiles.size() - b), chain);
       begin_gemm(2);
       for (const RowRange &r : bulk) {
         const int dw = std::min(64, r.w - d0), e0 = d0 + dw;
@@ -164,6 +165,9 @@ struct Builder {
     // panel; tile columns < bcast_tc belong to the next block column (part A)
     int row_tile0 = -1, bcast_tc = 0;
   };
+  // deep look-ahead on a top panel (mode 1): q tiles per row block; the tiles of the diagonal block of the next block
+  // column were already updated by its owner (skip them), those of the diagonal block after that join part A
+  int deep_q = 0;
   std::vector<Pending> pend;
   int mode = 0;                   // 0: Schur update; 1: trailing update of a block column (parts A / B); 2: chain GEMM (K = 64)
   const TopGroup *own = nullptr;  // mode 1 on a top panel: only the tile rows this rank owns
@@ -206,7 +210,12 @@ struct Builder {
               if ((g.tri & 1) && (tr + 1) * bm - 1 < tc * bn) continue;
               all_tiles += 1;
               if (own && own->owner((pd.row_tile0 + tr) * bm / own->rb) != D.rank) continue;
-              (tc < pd.bcast_tc ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
+              bool a = tc < pd.bcast_tc;
+              if (deep_q) {
+                if (tr < deep_q && tc < deep_q) continue;                                           // D(J+1): done early
+                if (tr >= deep_q && tr < 2 * deep_q && tc >= deep_q && tc < 2 * deep_q) a = true;   // D(J+2): needed early
+              }
+              (a ? pa : pb).push_back(TileRef{pd.prob, (uint16_t)tr, (uint16_t)tc});
             }
         flops += pd.flops;
       }
@@ -216,6 +225,7 @@ struct Builder {
       D.tiles.insert(D.tiles.end(), pa.begin(), pa.end());
       push_gemm(level, phase, cfg, b0, (int64_t)pa.size(), per_tile * (double)pa.size(), 0);
       depend(1, 0);  // the next chain may start as soon as part A is in place
+      if (deep_q) depend(3, 0);
       int64_t b1 = (int64_t)D.tiles.size();
       D.tiles.insert(D.tiles.end(), pb.begin(), pb.end());
       push_gemm(level, phase, cfg, b1, (int64_t)pb.size(), per_tile * (double)pb.size(), 0);
@@ -234,7 +244,7 @@ struct Builder {
           }
       flops += pd.flops;
     }
-    const int stream = mode == 2 ? 1 : 0;
+    const int stream = mode == 2 ? chain : 0;
     if (stream == 0) depend(0, 1);
     push_gemm(level, phase, cfg, begin, (int64_t)D.tiles.size() - begin, flops, stream);
   }
@@ -284,6 +294,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_NBO")) D.nbo = std::min(256, std::max(64, atoi(e) / 64 * 64));  // tuning knob: block-column width (single GPU)
   if (const char *e = getenv("CHOL_FUSED_ROWS_MAX")) D.fused_rows_max = D.fused_rows_max_top = atoi(e);
   if (const char *e = getenv("CHOL_FUSED_ROWS_MAX_TOP")) D.fused_rows_max_top = atoi(e);
+  if (const char *e = getenv("CHOL_DEEP")) D.deep = atoi(e) != 0;
   if (const char *e = getenv("CHOL_ROW_BLOCK")) D.row_block = std::min(kRowBlock, std::max(64, atoi(e) / 64 * 64));
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
@@ -402,6 +413,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
       h1 = h0 + (1 << (lvl - depth));
     }
     B.depend(1, 0);  // the chain of this level starts after the previous level's updates
+    B.depend(3, 0);
 
     if (!top) {
       int maxn = 0;
@@ -478,6 +490,87 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           const int rb = std::max(b * RB, below0), re = std::min((b + 1) * RB, R);
           if (re > rb) mine.push_back({rb, re});
         }
+        if (D.deep && D.lookahead) {
+          // ---- deep look-ahead: the chain of the diagonal blocks runs ahead of the group's row exchange.
+          // Stream 1: the owner of diagonal block J+1 solves ITS rows of block column J as soon as L(J,J) is there,
+          // applies them to its diagonal block (the last update it is missing), factors it and sends it out.
+          // Stream 3: every rank solves the rest of its rows of block column J and pushes them to the group.
+          // Stream 0: the trailing update of J waits for the group's rows, not for the diagonal chain.
+          const bool has_next = c1 < n;
+          const int next_owner = has_next ? grp.owner(J + 1) : -1;
+          const int w2 = has_next ? std::min(RB, n - c1) : 0;
+          auto diag_and_push = [&](int JJ, int cc0, int ww) {
+            B.chain = 1;
+            B.add_diag_slabs(B.add_panel_desc(base, ld, cc0, ww, P.start[p] + cc0, 0));
+            B.end_panel(lvl, phase);
+            int64_t rb = (int64_t)D.rects.size();
+            D.rects.push_back(RectDesc{base + cc0 + (int64_t)cc0 * ld, ld, ww, ww, 0, 0u, 0});
+            B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + JJ + 1, gmask & ~me, 1);
+          };
+          if (J == 0 && rank == diag_owner) diag_and_push(0, c0, w);  // (later diagonal blocks were factored one step ahead)
+          std::vector<std::pair<int, int>> early, rest;
+          for (auto &rg : mine) (rank == next_owner && rg.first / RB == J + 1 ? early : rest).push_back(rg);
+          if (rank == next_owner) {
+            if (rank != diag_owner) B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
+            B.chain = 1;
+            if (!early.empty()) {
+              const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
+              for (auto &rg : early) B.add_row_slabs(desc, rg.first, rg.second);
+              B.end_panel(lvl, phase);
+            }
+            B.depend(3, 1);  // the rows stream pushes these rows along with the rest
+            B.begin_gemm(2);
+            // (all rows of row block J+1: below a narrower last diagonal block they are off-diagonal rows, which the
+            // trailing update skips along with the diagonal block's)
+            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, std::min(RB, R - c1), w2, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld,
+                          ld, w);
+            B.end_gemm(lvl, phase, false);
+            diag_and_push(J + 1, c1, w2);
+          }
+          B.chain = 3;
+          if (rank == diag_owner) B.depend(3, 1);  // (its own diagonal block: stream order of stream 1)
+          else B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 3);
+          for (auto &rg : rest) B.bulk.push_back(Builder::RowRange{base, ld, c0, w, rg.first, rg.second});
+          if (B.bulk_slabs() <= D.fused_rows_max_top) {
+            if (!rest.empty()) {
+              const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
+              for (auto &rg : rest) B.add_row_slabs(desc, rg.first, rg.second);
+              B.end_panel(lvl, phase);
+            }
+            B.bulk.clear();
+          } else
+            B.emit_bulk_rows(lvl, phase);
+          B.chain = 1;
+          {
+            int64_t rb = (int64_t)D.rects.size();
+            for (auto &rg : mine)
+              if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
+            B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 3);
+          }
+          {
+            B.depend(2, 3);
+            int64_t rb = (int64_t)D.rects.size();
+            for (auto &rg : mine)
+              if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
+            B.push_rects(lvl, phase, rb, wmask & ~gmask, 0, 0, 0, 2);
+            rb = (int64_t)D.rects.size();
+            for (auto &rg : mine)
+              if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri, 0u, 0});
+            B.push_rects(lvl, phase, rb, wmask & ~me, 0, 0, 0, 2);
+          }
+          B.depend(0, 3);
+          B.sync(lvl, phase, SLOT_GROUP, lvl_seq + J + 1, 0, gmask & ~me, 0);
+          B.begin_gemm(1);
+          if (has_next) {
+            const int next_tc = (w2 + 63) / 64;
+            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, R - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, w,
+                          c1 / 64, next_tc);
+          }
+          B.deep_q = RB / 64;
+          B.end_gemm(lvl, phase, false);
+          B.deep_q = 0;
+          continue;
+        }
         if (rank == diag_owner) {  // the diagonal block (w x w), then out to every rank
           B.add_diag_slabs(B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 0));
           B.end_panel(lvl, phase);
@@ -531,6 +624,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
       // every rank holds the complete panels of the level once all pushes have landed
       B.depend(0, 1);
       B.depend(0, 2);
+      B.depend(0, 3);
       B.sync(lvl, PH_UPDATE, SLOT_WORLD, lvl_seq + 1, wmask & ~me, wmask & ~me, 0);
       h0 = 1 << lvl, h1 = 1 << (lvl + 1);  // the Schur updates below take contributions from every panel of the level
     }
@@ -639,6 +733,7 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   // the step ends on stream 0
   B.depend(0, 1);
   B.depend(0, 2);
+  B.depend(0, 3);
   if (B.pendw[0] >= 0) B.push(Builder::mk(K_NOP, 0, 0), 0);
   if (D.contribs.size() > 0x7fffffffULL || D.probs.size() > 0x7fffffffULL) return err = "schedule too large", -1;
   return 0;

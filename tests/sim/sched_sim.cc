@@ -31,7 +31,7 @@ struct Rank {
   std::vector<double> fac;
   unsigned long long flags[kFlagSlots][kPeers];
   std::vector<std::vector<int>> q;   // launch indices per stream
-  size_t head[3] = {0, 0, 0};
+  size_t head[4] = {0, 0, 0, 0};
   std::vector<char> ev;              // event recorded?
   std::vector<char> signalled;       // K_SYNC: signals already sent
 };
@@ -80,7 +80,7 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
     for (int64_t e = 0; e < P.nz; e++)
       if (k.D.a_off[e] >= 0) k.fac[k.D.a_off[e]] = P.ev[e];
     memset(k.flags, 0, sizeof k.flags);
-    k.q.assign(3, {});
+    k.q.assign(4, {});
     for (size_t i = 0; i < k.D.launches.size(); i++) k.q[k.D.launches[i].stream].push_back((int)i);
     k.ev.assign(k.D.num_events, 0);
     k.signalled.assign(k.D.launches.size(), 0);
@@ -187,17 +187,17 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
   // Adversarial interleavings: every (rank, stream) queue gets a heavy-tailed weight per seed, so some queues
   // race far ahead of the others whenever nothing holds them back (uniform picks keep the ranks in near
   // lock step and hide missing waits).
-  double weight[kPeers][3];
+  double weight[kPeers][4];
   {
     std::normal_distribution<double> nd(0.0, 1.0);
     for (int r = 0; r < kPeers; r++)
-      for (int s = 0; s < 3; s++) weight[r][s] = std::exp(4.0 * nd(rng));
+      for (int s = 0; s < 4; s++) weight[r][s] = std::exp(4.0 * nd(rng));
   }
   std::vector<std::pair<int, int>> ready;
   while (remaining) {
     ready.clear();
     for (int r = 0; r < world; r++)
-      for (int s = 0; s < 3; s++) {
+      for (int s = 0; s < 4; s++) {
         Rank &k = R[r];
         if (k.head[s] >= k.q[s].size()) continue;
         const int li = k.q[s][k.head[s]];
@@ -219,7 +219,7 @@ extern "C" int sim_factor(int nx, int ny, int nz, int stencil, int levels, int w
     if (ready.empty()) {
       std::string m = "deadlock: heads";
       for (int r = 0; r < world; r++)
-        for (int s = 0; s < 3; s++)
+        for (int s = 0; s < 4; s++)
           if (R[r].head[s] < R[r].q[s].size()) {
             const Launch &l = R[r].D.launches[R[r].q[s][R[r].head[s]]];
             m += " [rank " + std::to_string(r) + " stream " + std::to_string(s) + " kind " + std::to_string(l.kind) + " level " + std::to_string(l.level) +

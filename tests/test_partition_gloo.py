@@ -90,8 +90,10 @@ def test_partition_covers_single_rank_schedule(world):
         assert kinds.count("reduce_rects") == depth
         assert r["stats"]["push_launches"] > 0
         assert r["stats"]["top_doubles"] == ranks[0]["stats"]["top_doubles"] > 0
-        # streams: chain kernels on 1, background pushes on 2, everything else on 0
-        assert {l["stream"] for l in r["launches"] if l["kind"] == "panel_kernel"} == {1}
+        # streams: the chain of the diagonal blocks on 1, the rows of the top panels on 3, background pushes on 2,
+        # trailing and Schur updates and the reductions on 0
+        assert {l["stream"] for l in r["launches"] if l["kind"] == "panel_kernel"} == {1, 3}
+        assert {l["stream"] for l in r["launches"] if l["kind"] == "panel_kernel" and l["level"] >= depth} == {1}
         assert {l["stream"] for l in r["launches"] if l["kind"] == "reduce_rects"} == {0}
     nsync = [sum(l["kind"] == "peer_sync" for l in r["launches"]) for r in ranks]
     assert min(nsync) >= 2 + depth
