@@ -23,7 +23,7 @@ def main():
     ch = Cholesky().generate(*WORKLOADS[workload]).analyze()
     ms = {}
     for line in open(report):
-        m = re.match(r"\| (\w+) \| (\d+) \| ([\w+]+) \| (\d+) \| (\d+) \| ([\d.]+) \|", line)
+        m = re.match(r"\| ([\w/]+) \| (\d+) \| ([\w+]+) \| (\d+) \| (\d+) \| ([\d.]+) \|", line)
         if m:
             _, lvl, ph, _, _, t = m.groups()
             d = ms.setdefault(int(lvl), {"chain": 0.0, "update": 0.0})
