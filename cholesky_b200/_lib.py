@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libcholesky_b200.so")
 # every symbol include/cholesky.h, include/chol_mmio.h and include/chol_mnd.h declare
 EXPORTS = [
     "chol_create", "chol_num_ranks", "chol_rank_handle", "chol_destroy", "chol_last_error", "register_mappers", "chol_load", "chol_load_arrays",
-    "chol_generate", "chol_write_inputs", "chol_analyze", "chol_n", "chol_nz", "chol_levels",
+    "chol_generate", "chol_write_inputs", "chol_analyze", "chol_save_analysis", "chol_load_analysis", "chol_n", "chol_nz", "chol_levels",
     "chol_num_separators", "chol_max_int_size", "chol_num_blocks", "chol_num_clusters0", "chol_get_perm",
     "chol_get_sep_sizes", "chol_get_block_bounds", "chol_num_filled", "chol_get_filled", "chol_filled_checksum",
     "chol_flops", "chol_flops_by_level", "chol_call_counts", "chol_factor_doubles", "chol_level_bytes", "chol_assemble", "chol_factor",

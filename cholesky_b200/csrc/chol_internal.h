@@ -75,6 +75,9 @@ struct Symbolic {
 };
 
 int analyze(const Problem &P, Symbolic &S, bool keep_records, std::string &err);
+// the symbolic structure as one binary file (factor_file.cc): the ranks of a node analyse once and share the result
+int save_symbolic(const Problem &P, const Symbolic &S, const char *path, std::string &err);
+int load_symbolic(const Problem &P, Symbolic &S, const char *path, std::string &err);
 
 // ----------------------------------------------------------------------------- schedule
 // Everything the device executes is one of three grouped kernels over descriptor arrays.

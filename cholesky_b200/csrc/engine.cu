@@ -292,6 +292,29 @@ int chol_analyze(chol_t *c, int keep_records) {
   return 0;
 }
 
+/* the symbolic analysis as a file: one rank of a node analyses and saves, the others load instead of repeating the
+ * analysis (same result: the schedules built from it are identical; the file is checked against the loaded problem) */
+int chol_save_analysis(chol_t *c, const char *path) {
+  if (!c->analyzed) return fail(c, "analyze first");
+  return save_symbolic(c->P, c->S, path, c->err) ? -1 : 0;
+}
+int chol_load_analysis(chol_t *c, const char *path) {
+  if (c->parent) return fail(c, "analyze through the group handle");
+  if (!c->loaded) return fail(c, "load a problem first");
+  free_device(c);
+  c->analyzed = false;
+  if (load_symbolic(c->P, c->S, path, c->err)) return -1;
+  if (is_group(c)) {
+    for (size_t i = 0; i < c->sub.size(); i++) {
+      if (build_schedule(c->P, c->S, c->sub[i]->D, (int)i, (int)c->sub.size(), false, c->sub[i]->err)) return fail(c, c->sub[i]->err);
+      c->sub[i]->loaded = c->sub[i]->analyzed = true;
+    }
+  } else if (build_schedule(c->P, c->S, c->D, c->rank, c->world, false, c->err))
+    return -1;
+  c->analyzed = true;
+  return 0;
+}
+
 int chol_n(chol_t *c) { return c->P.n; }
 int64_t chol_nz(chol_t *c) { return c->P.nz; }
 int chol_levels(chol_t *c) { return c->P.levels; }

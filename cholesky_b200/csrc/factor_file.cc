@@ -8,6 +8,7 @@
 //   record  : int32 row0, col0, nrows, ncols (global permuted, 0-based); double v[nrows * ncols], column-major
 //
 // The converter never holds more than one record: pass 1 is the header's count, pass 2 prints.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -69,6 +70,94 @@ int write_factor_binary(const Problem &P, const Symbolic &S, const double *fac, 
   fwrite(&h, sizeof h, 1, f);
   const bool bad = ferror(f) != 0;
   if (fclose(f) != 0 || bad) return err = std::string("write error on ") + path, -1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The symbolic structure as one binary file.  With one process per GPU every rank of a node needs the same
+// Symbolic; one of them analyses (all host threads) and the others read the result instead of repeating the
+// analysis side by side on a share of the cores (8 ranks: 7.6 s of analysis each).  A stamp of the problem
+// (sizes, separator sizes, number of entries) guards against reading the analysis of a different problem.
+namespace {
+const char kSymMagic[8] = {'C', 'H', 'O', 'L', 'S', 'Y', 'M', '1'};
+template <typename T>
+bool put(FILE *f, const std::vector<T> &v) {
+  const uint64_t n = v.size();
+  return fwrite(&n, sizeof n, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <typename T>
+bool get(FILE *f, std::vector<T> &v) {
+  uint64_t n = 0;
+  if (fread(&n, sizeof n, 1, f) != 1 || n > (1ULL << 36)) return false;
+  v.resize(n);
+  return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+uint64_t problem_stamp(const Problem &P) {
+  uint64_t h = mix64((uint64_t)P.n) ^ mix64((uint64_t)P.nz + 17) ^ mix64((uint64_t)P.levels + 31);
+  for (int i = 1; i <= P.N; i++) h = mix64(h ^ (uint64_t)P.sz[i]);
+  for (size_t e = 0; e < P.ei.size(); e += std::max<size_t>(1, P.ei.size() / 4096)) h = mix64(h ^ ((uint64_t)P.ei[e] << 32) ^ (uint64_t)P.ej[e]);
+  return h;
+}
+}  // namespace
+
+int save_symbolic(const Problem &P, const Symbolic &S, const char *path, std::string &err) {
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return err = std::string("cannot write ") + tmp, -1;
+  const uint64_t stamp = problem_stamp(P);
+  std::vector<int> flat, ptr;  // cb[h][k][j], flattened
+  ptr.push_back(0);
+  std::vector<int> nk((size_t)P.N + 2, 0);
+  for (int h = 1; h <= P.N; h++) {
+    nk[h] = (int)S.cb[h].size();
+    for (const auto &lst : S.cb[h]) {
+      flat.insert(flat.end(), lst.begin(), lst.end());
+      ptr.push_back((int)flat.size());
+    }
+  }
+  int64_t scal[7] = {S.total_doubles, S.nblocks, S.nclusters0, S.calls[0], S.calls[1], S.calls[2], S.calls[3]};
+  bool ok = fwrite(kSymMagic, 8, 1, f) == 1 && fwrite(&stamp, 8, 1, f) == 1 && fwrite(scal, sizeof scal, 1, f) == 1 && put(f, nk) && put(f, ptr) &&
+            put(f, flat) && put(f, S.seg_ptr) && put(f, S.segs) && put(f, S.rows) && put(f, S.ld) && put(f, S.poff) && put(f, S.nfilled) &&
+            put(f, S.checksum) && put(f, S.f_potrf) && put(f, S.f_trsm) && put(f, S.f_syrk) && put(f, S.f_gemm);
+  const uint64_t nrec = S.records.size();
+  ok = ok && fwrite(&nrec, 8, 1, f) == 1;
+  for (const auto &r : S.records) ok = ok && put(f, r);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) return err = std::string("write error on ") + path, -1;  // readers never see a partial file
+  return 0;
+}
+
+int load_symbolic(const Problem &P, Symbolic &S, const char *path, std::string &err) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return err = std::string("cannot read ") + path, -1;
+  S = Symbolic();
+  char magic[8];
+  uint64_t stamp = 0, nrec = 0;
+  int64_t scal[7];
+  std::vector<int> flat, ptr, nk;
+  bool ok = fread(magic, 8, 1, f) == 1 && !memcmp(magic, kSymMagic, 8) && fread(&stamp, 8, 1, f) == 1 && fread(scal, sizeof scal, 1, f) == 1 &&
+            get(f, nk) && get(f, ptr) && get(f, flat) && get(f, S.seg_ptr) && get(f, S.segs) && get(f, S.rows) && get(f, S.ld) && get(f, S.poff) &&
+            get(f, S.nfilled) && get(f, S.checksum) && get(f, S.f_potrf) && get(f, S.f_trsm) && get(f, S.f_syrk) && get(f, S.f_gemm) &&
+            fread(&nrec, 8, 1, f) == 1 && nrec <= 64;
+  if (ok) {
+    S.records.resize(nrec);
+    for (auto &r : S.records) ok = ok && get(f, r);
+  }
+  fclose(f);
+  if (!ok) return err = std::string(path) + " is not a symbolic-analysis file (or is truncated)", -1;
+  if (stamp != problem_stamp(P) || (int)nk.size() != P.N + 2 || (int)S.rows.size() != P.N + 2)
+    return err = std::string(path) + " holds the analysis of a different problem", -1;
+  S.total_doubles = scal[0], S.nblocks = scal[1], S.nclusters0 = scal[2];
+  for (int i = 0; i < 4; i++) S.calls[i] = scal[3 + i];
+  S.cb.assign((size_t)P.N + 2, {});
+  size_t q = 0;
+  for (int h = 1; h <= P.N; h++) {
+    S.cb[h].resize(nk[h]);
+    for (int k = 0; k < nk[h]; k++, q++) {
+      if (q + 1 >= ptr.size() || ptr[q] > ptr[q + 1] || (size_t)ptr[q + 1] > flat.size()) return err = std::string(path) + " is corrupt", -1;
+      S.cb[h][k].assign(flat.begin() + ptr[q], flat.begin() + ptr[q + 1]);
+    }
+  }
   return 0;
 }
 

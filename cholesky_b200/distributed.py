@@ -8,6 +8,7 @@ through torch or NCCL: after the ranks have exchanged the CUDA-IPC handles of th
 push factored rows into the peers' copies and meet in flag words, all through NVLink peer memory (csrc/kernels.cuh).
 """
 import os
+import tempfile
 
 import torch
 import torch.distributed as dist
@@ -16,10 +17,13 @@ from .engine import Cholesky
 
 
 def make_partitioned(grid=None, files=None, keep_records=False):
-    """build this rank's engine: generate/load, set the partition, analyse"""
+    """build this rank's engine: generate/load, set the partition, analyse.  The symbolic analysis is the same on
+    every rank, so rank 0 runs it with all the host threads and hands the result to the others through a file in
+    shared memory (CHOL_SHARE_ANALYSIS=0: every rank analyses for itself, side by side on a share of the cores)"""
     rank, world = dist.get_rank(), dist.get_world_size()
-    # the ranks of one node share its host cores for the symbolic analysis
-    os.environ.setdefault("CHOL_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // world))))
+    share = world > 1 and os.environ.get("CHOL_SHARE_ANALYSIS", "1") != "0"
+    if not share:  # the ranks of one node share its host cores
+        os.environ.setdefault("CHOL_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // world))))
     dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
     ch = Cholesky(dev)
     if grid is not None:
@@ -27,7 +31,20 @@ def make_partitioned(grid=None, files=None, keep_records=False):
     else:
         ch.load(*files)
     ch.set_partition(rank, world)
-    ch.analyze(keep_records=keep_records)
+    if not share:
+        return ch.analyze(keep_records=keep_records)
+    box = [None]
+    if rank == 0:
+        ch.analyze(keep_records=keep_records)
+        d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        box[0] = os.path.join(d, f"chol_analysis_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}.bin")
+        ch.save_analysis(box[0])
+    dist.broadcast_object_list(box, 0)
+    if rank != 0:
+        ch.load_analysis(box[0])
+    dist.barrier()
+    if rank == 0:
+        os.unlink(box[0])
     return ch
 
 

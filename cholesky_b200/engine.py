@@ -86,6 +86,21 @@ class Cholesky:
         self.num_separators = self.L.chol_num_separators(self.h)
         return self
 
+    def _after_analyze(self):
+        self.n = self.L.chol_n(self.h)
+        self.nz = int(self.L.chol_nz(self.h))
+        self.levels = self.L.chol_levels(self.h)
+        self.num_separators = self.L.chol_num_separators(self.h)
+        return self
+
+    def save_analysis(self, path):
+        """the symbolic analysis as a file (the other ranks of a node load it instead of analysing again)"""
+        self._ck(self.L.chol_save_analysis(self.h, path.encode()))
+
+    def load_analysis(self, path):
+        self._ck(self.L.chol_load_analysis(self.h, path.encode()))
+        return self._after_analyze()
+
     def perm(self):
         out = np.zeros(self.n, dtype=np.int32)
         self.L.chol_get_perm(self.h, _p(out))

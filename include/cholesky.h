@@ -73,6 +73,11 @@ int chol_write_inputs(chol_t *, const char *matrix_mtx, const char *separators_t
  * keep_records != 0 keeps every Filled record for chol_get_filled (counts and checksums are
  * always kept). */
 int chol_analyze(chol_t *, int keep_records);
+/* the result of chol_analyze as a file, so that the ranks of a node (one process per GPU) analyse once: one rank
+ * calls chol_analyze + chol_save_analysis, the others chol_load_analysis instead of chol_analyze (after loading the
+ * same problem and setting their partition; the file is refused if it belongs to a different problem) */
+int chol_save_analysis(chol_t *, const char *path);
+int chol_load_analysis(chol_t *, const char *path);
 int chol_n(chol_t *);
 int64_t chol_nz(chol_t *);
 int chol_levels(chol_t *);

@@ -305,3 +305,40 @@ def test_block_pattern_is_bit_exact_at_the_baseline_sizes(grid, tmp_path):
     finally:
         oc.close()
         shutil.rmtree(d)
+
+
+def test_analysis_file_round_trip(tmp_path):
+    """chol_save_analysis / chol_load_analysis: the ranks of a node analyse once.  A handle that loads the file compiles
+    the same schedule as one that analysed for itself; the file of a different problem is refused"""
+    from cholesky_b200 import CholeskyError
+    grid = (20, 18, 16, 7, 5)
+    a = Cholesky().generate(*grid).analyze(keep_records=True)
+    path = str(tmp_path / "analysis.bin")
+    a.save_analysis(path)
+    for rank, world in ((0, 1), (1, 2), (3, 4)):
+        own = Cholesky().generate(*grid).set_partition(rank, world).analyze(keep_records=True)
+        b = Cholesky().generate(*grid).set_partition(rank, world).load_analysis(path)
+        assert b.launches() == own.launches()
+        assert b.partition_stats() == own.partition_stats()
+        assert b.flops() == own.flops() and b.call_counts() == own.call_counts() and b.factor_doubles() == own.factor_doubles()
+        for t in range(b.levels):
+            assert b.filled_checksum(t) == own.filled_checksum(t)
+            assert np.array_equal(b.filled(t), own.filled(t))
+    with pytest.raises(CholeskyError, match="different problem"):
+        Cholesky().generate(20, 18, 17, 7, 5).load_analysis(path)
+    (tmp_path / "junk.bin").write_bytes(b"not an analysis")
+    with pytest.raises(CholeskyError):
+        Cholesky().generate(*grid).load_analysis(str(tmp_path / "junk.bin"))
+
+
+def test_create_refuses_unsupported_gpu_counts():
+    """chol_create(devices, ngpu): 1, 2, 4 or 8 GPUs -- never silently fewer than asked for"""
+    from cholesky_b200 import CholeskyError
+    for bad in ([0, 1, 2], [0] * 5, [0] * 16):
+        with pytest.raises(CholeskyError):
+            Cholesky(devices=bad)
+    g = Cholesky(devices=[0, 0, 0, 0])       # creating a group touches no device
+    assert g.num_ranks() == 4
+    g.generate(12, 12, 12, 7, 4).analyze()   # one symbolic analysis, four schedules
+    stats = [g.rank_handle(r).partition_stats() for r in range(4)]
+    assert sum(s["assembled"] for s in stats) == g.nz
