@@ -28,7 +28,6 @@
 
 using namespace chb;
 
-constexpr int kMaxDevices = 16;
 constexpr int kStreams = 4;  // update stream, chain stream (look-ahead), background pushes, rows stream (top panels of a partition)
 
 struct SolveDev;
