@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_warp(const GemmPr
 constexpr int kNB = 64;
 constexpr int kPanelThreads = 256;
 constexpr int kLdx = kNB + 4;
-constexpr long long kSpinLimit = 6000000000LL;  // ~3 s at 2 GHz: a wait gives up and raises an error code instead of hanging the GPU
+constexpr long long kSpinLimit = 16000000000LL;  // ~8 s at 2 GHz: a wait gives up and raises an error code instead of hanging the GPU
 inline size_t panel_smem_bytes(int wmax) { return ((size_t)((wmax + kNB - 1) / kNB * kNB) * kLdx + (size_t)kNB * kLdx + kNB) * sizeof(double); }
 
 // Cholesky of the 64 x 64 tile T (entry (i, c) at T[c * kLdx + i]) in shared memory, right-looking in panels of
