@@ -58,6 +58,19 @@ def test_simulated_schedule_with_the_throughput_path_for_the_rows(monkeypatch, w
     assert ok and copy_diff == 0.0, worst
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_simulated_top_levels_with_the_throughput_path_for_the_rows(monkeypatch, world):
+    """CHOL_FUSED_ROWS_MAX_TOP=0: on the top panels of a partition the rows below the diagonal blocks go through
+    trsm_tile + grouped GEMM launches on the rows stream (what a rank does when it owns more than two waves of slabs)"""
+    monkeypatch.setenv("CHOL_ROW_BLOCK", "64")
+    monkeypatch.setenv("CHOL_FUSED_ROWS_MAX_TOP", "0")
+    grid = (20, 20, 20, 7, 5)
+    for seed in (1, 2, 3):
+        L, copy_diff, _ = sim.factor(grid, world, seed)
+        ok, worst = entrywise_ok(L, oracle_factor(grid))
+        assert ok and copy_diff == 0.0, worst
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_simulated_schedule_without_deep_lookahead(monkeypatch, world):
     """CHOL_DEEP=0: the diagonal block of a top panel is factored after the trailing update of the previous block
