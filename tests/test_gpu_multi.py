@@ -47,6 +47,16 @@ def test_group_handle_matches_oracle(world, grid, row_block):
     assert max(out["push_launches"]) > 0      # rows of the top panels were pushed to peers (a rank that owns no block of a tiny panel pushes nothing)
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_group_handle_with_the_throughput_path_on_the_top_panels(world):
+    """CHOL_FUSED_ROWS_MAX_TOP=0: the rows below the diagonal blocks of the top panels go through trsm_tile + grouped GEMM
+    launches on the rows stream (what a rank does when it owns more than two waves of 64-row slabs of a block column)"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    env = dict(os.environ, CHOL_ROW_BLOCK="64", CHOL_FUSED_ROWS_MAX_TOP="0", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    _run([sys.executable, os.path.join(ROOT, "tests", "group_worker.py"), "33,31,29,7,5", ",".join(["0"] * world)], env)
+
+
 @pytest.mark.parametrize("world,grid,row_block", [(2, "30,30,30,7,4", 64), (4, "48,48,48,7,0", 256), (8, "64,64,64,7,0", 256)])
 def test_group_handle_on_distinct_gpus(world, grid, row_block):
     """one process, one rank per GPU (cudaDeviceEnablePeerAccess, no IPC)"""
