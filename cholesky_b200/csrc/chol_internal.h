@@ -182,7 +182,6 @@ struct Schedule {
   bool lookahead = true;      // chain kernels on a second stream, overlapping the trailing updates (CHOL_LOOKAHEAD=0: off)
   int num_events = 0;         // cross-stream events the launch list refers to
   int64_t top_doubles = 0;    // leading part of the factor buffer that holds the top panels (one copy per rank)
-  bool deep = true;           // top panels: the chain of the diagonal blocks runs ahead of the group's row exchange (CHOL_DEEP=0: off)
   int row_block = kRowBlock;  // rows of a top panel are dealt to its group in blocks of this many (= block-column width there)
 };
 

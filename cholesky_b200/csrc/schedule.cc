@@ -25,9 +25,11 @@
 //   * after level d one K_REDUCE per rank sums the group's partial sums of the rows it owns (peer loads);
 //   * per 256-wide block column J of a top panel: the owner of the diagonal block factors it and pushes
 //     it to every rank (peer stores + flag SLOT_DIAG); every rank of the group solves its own rows
-//     below it, pushes the pivot-block part of them to the group (flag SLOT_GROUP, the trailing update
-//     needs them as its B operand) and, on a background stream, everything else to everybody; then
-//     each rank updates its own rows of the trailing matrix (parts A / B as above);
+//     below it (stream 3), pushes the pivot-block part of them to the group (flag SLOT_GROUP, the trailing
+//     update needs them as its B operand) and, on a background stream, everything else to everybody; then
+//     each rank updates its own rows of the trailing matrix (parts A / B as above, stream 0).  The chain
+//     of the diagonal blocks (stream 1) runs one block column ahead: the owner of diagonal block J + 1
+//     solves its rows of block column J first, applies them to its diagonal block, factors and sends it;
 //   * after a top level a world barrier (all pushed rows have landed: every rank now holds the complete
 //     factored panels of the level), then its Schur updates, each destination row block computed by
 //     its owner from its local copies.
@@ -294,7 +296,6 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
   if (const char *e = getenv("CHOL_NBO")) D.nbo = std::min(256, std::max(64, atoi(e) / 64 * 64));  // tuning knob: block-column width (single GPU)
   if (const char *e = getenv("CHOL_FUSED_ROWS_MAX")) D.fused_rows_max = D.fused_rows_max_top = atoi(e);
   if (const char *e = getenv("CHOL_FUSED_ROWS_MAX_TOP")) D.fused_rows_max_top = atoi(e);
-  if (const char *e = getenv("CHOL_DEEP")) D.deep = atoi(e) != 0;
   if (const char *e = getenv("CHOL_ROW_BLOCK")) D.row_block = std::min(kRowBlock, std::max(64, atoi(e) / 64 * 64));
   if (split_phases) D.lookahead = false;  // the piecewise entry points run one phase of one level at a time
   const int L = P.levels, N = P.N;
@@ -490,116 +491,65 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
           const int rb = std::max(b * RB, below0), re = std::min((b + 1) * RB, R);
           if (re > rb) mine.push_back({rb, re});
         }
-        if (D.deep && D.lookahead) {
-          // ---- deep look-ahead: the chain of the diagonal blocks runs ahead of the group's row exchange.
-          // Stream 1: the owner of diagonal block J+1 solves ITS rows of block column J as soon as L(J,J) is there,
-          // applies them to its diagonal block (the last update it is missing), factors it and sends it out.
-          // Stream 3: every rank solves the rest of its rows of block column J and pushes them to the group.
-          // Stream 0: the trailing update of J waits for the group's rows, not for the diagonal chain.
-          const bool has_next = c1 < n;
-          const int next_owner = has_next ? grp.owner(J + 1) : -1;
-          const int w2 = has_next ? std::min(RB, n - c1) : 0;
-          auto diag_and_push = [&](int JJ, int cc0, int ww) {
-            B.chain = 1;
-            B.add_diag_slabs(B.add_panel_desc(base, ld, cc0, ww, P.start[p] + cc0, 0));
-            B.end_panel(lvl, phase);
-            int64_t rb = (int64_t)D.rects.size();
-            D.rects.push_back(RectDesc{base + cc0 + (int64_t)cc0 * ld, ld, ww, ww, 0, 0u, 0});
-            B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + JJ + 1, gmask & ~me, 1);
-          };
-          if (J == 0 && rank == diag_owner) diag_and_push(0, c0, w);  // (later diagonal blocks were factored one step ahead)
-          std::vector<std::pair<int, int>> early, rest;
-          for (auto &rg : mine) (rank == next_owner && rg.first / RB == J + 1 ? early : rest).push_back(rg);
-          if (rank == next_owner) {
-            if (rank != diag_owner) B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
-            B.chain = 1;
-            if (!early.empty()) {
-              const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
-              for (auto &rg : early) B.add_row_slabs(desc, rg.first, rg.second);
-              B.end_panel(lvl, phase);
-            }
-            B.depend(3, 1);  // the rows stream pushes these rows along with the rest
-            B.begin_gemm(2);
-            // (all rows of row block J+1: below a narrower last diagonal block they are off-diagonal rows, which the
-            // trailing update skips along with the diagonal block's)
-            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, std::min(RB, R - c1), w2, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld,
-                          ld, w);
-            B.end_gemm(lvl, phase, false);
-            diag_and_push(J + 1, c1, w2);
-          }
-          B.chain = 3;
-          if (rank == diag_owner) B.depend(3, 1);  // (its own diagonal block: stream order of stream 1)
-          else B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 3);
-          for (auto &rg : rest) B.bulk.push_back(Builder::RowRange{base, ld, c0, w, rg.first, rg.second});
-          if (B.bulk_slabs() <= D.fused_rows_max_top) {
-            if (!rest.empty()) {
-              const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
-              for (auto &rg : rest) B.add_row_slabs(desc, rg.first, rg.second);
-              B.end_panel(lvl, phase);
-            }
-            B.bulk.clear();
-          } else
-            B.emit_bulk_rows(lvl, phase);
+        // ---- the chain of the diagonal blocks runs ahead of the group's row exchange (deep look-ahead; the version
+        // that factored diagonal block J+1 after the trailing update of J: 158.3 ms on 8 GPUs against 154.1).
+        // Stream 1: the owner of diagonal block J+1 solves ITS rows of block column J as soon as L(J,J) is there,
+        // applies them to its diagonal block (the last update it is missing), factors it and sends it out.
+        // Stream 3: every rank solves the rest of its rows of block column J and pushes them to the group.
+        // Stream 0: the trailing update of J waits for the group's rows, not for the diagonal chain.
+        const bool has_next = c1 < n;
+        const int next_owner = has_next ? grp.owner(J + 1) : -1;
+        const int w2 = has_next ? std::min(RB, n - c1) : 0;
+        auto diag_and_push = [&](int JJ, int cc0, int ww) {
           B.chain = 1;
-          {
-            int64_t rb = (int64_t)D.rects.size();
-            for (auto &rg : mine)
-              if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
-            B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 3);
-          }
-          {
-            B.depend(2, 3);
-            int64_t rb = (int64_t)D.rects.size();
-            for (auto &rg : mine)
-              if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
-            B.push_rects(lvl, phase, rb, wmask & ~gmask, 0, 0, 0, 2);
-            rb = (int64_t)D.rects.size();
-            for (auto &rg : mine)
-              if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri, 0u, 0});
-            B.push_rects(lvl, phase, rb, wmask & ~me, 0, 0, 0, 2);
-          }
-          B.depend(0, 3);
-          B.sync(lvl, phase, SLOT_GROUP, lvl_seq + J + 1, 0, gmask & ~me, 0);
-          B.begin_gemm(1);
-          if (has_next) {
-            const int next_tc = (w2 + 63) / 64;
-            B.add_problem(base + c1 + (int64_t)c1 * ld, ld, R - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, w,
-                          c1 / 64, next_tc);
-          }
-          B.deep_q = RB / 64;
-          B.end_gemm(lvl, phase, false);
-          B.deep_q = 0;
-          continue;
-        }
-        if (rank == diag_owner) {  // the diagonal block (w x w), then out to every rank
-          B.add_diag_slabs(B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 0));
+          B.add_diag_slabs(B.add_panel_desc(base, ld, cc0, ww, P.start[p] + cc0, 0));
           B.end_panel(lvl, phase);
           int64_t rb = (int64_t)D.rects.size();
-          D.rects.push_back(RectDesc{base + c0 + (int64_t)c0 * ld, ld, w, w, 0, 0u, 0});
-          B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + J + 1, gmask & ~me, 1);
-        } else
-          B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
-        // own rows below: X <- X L_JJ^-T (the diagonal block is final in this rank's copy by now)
-        for (auto &rg : mine) B.bulk.push_back(Builder::RowRange{base, ld, c0, w, rg.first, rg.second});
-        if (B.bulk_slabs() <= D.fused_rows_max_top) {
-          if (!mine.empty()) {
+          D.rects.push_back(RectDesc{base + cc0 + (int64_t)cc0 * ld, ld, ww, ww, 0, 0u, 0});
+          B.push_rects(lvl, phase, rb, wmask & ~me, SLOT_DIAG, lvl_seq + JJ + 1, gmask & ~me, 1);
+        };
+        if (J == 0 && rank == diag_owner) diag_and_push(0, c0, w);  // (later diagonal blocks were factored one step ahead)
+        std::vector<std::pair<int, int>> early, rest;
+        for (auto &rg : mine) (rank == next_owner && rg.first / RB == J + 1 ? early : rest).push_back(rg);
+        if (rank == next_owner) {
+          if (rank != diag_owner) B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 1);
+          B.chain = 1;
+          if (!early.empty()) {
             const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
-            for (auto &rg : mine) B.add_row_slabs(desc, rg.first, rg.second);
+            for (auto &rg : early) B.add_row_slabs(desc, rg.first, rg.second);
+            B.end_panel(lvl, phase);
+          }
+          B.depend(3, 1);  // the rows stream pushes these rows along with the rest
+          B.begin_gemm(2);
+          // (all rows of row block J+1: below a narrower last diagonal block they are off-diagonal rows, which the
+          // trailing update skips along with the diagonal block's)
+          B.add_problem(base + c1 + (int64_t)c1 * ld, ld, std::min(RB, R - c1), w2, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld,
+                        ld, w);
+          B.end_gemm(lvl, phase, false);
+          diag_and_push(J + 1, c1, w2);
+        }
+        B.chain = 3;
+        if (rank == diag_owner) B.depend(3, 1);  // (its own diagonal block: stream order of stream 1)
+        else B.sync(lvl, phase, SLOT_DIAG, lvl_seq + J + 1, 0, 1u << diag_owner, 3);
+        for (auto &rg : rest) B.bulk.push_back(Builder::RowRange{base, ld, c0, w, rg.first, rg.second});
+        if (B.bulk_slabs() <= D.fused_rows_max_top) {
+          if (!rest.empty()) {
+            const int desc = B.add_panel_desc(base, ld, c0, w, P.start[p] + c0, 1);
+            for (auto &rg : rest) B.add_row_slabs(desc, rg.first, rg.second);
             B.end_panel(lvl, phase);
           }
           B.bulk.clear();
         } else
           B.emit_bulk_rows(lvl, phase);
-        // the group needs the pivot-block rows of this block column for its trailing updates: push them now ...
+        B.chain = 1;
         {
           int64_t rb = (int64_t)D.rects.size();
           for (auto &rg : mine)
             if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
-          B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 1);
+          B.push_rects(lvl, phase, rb, gmask & ~me, SLOT_GROUP, lvl_seq + J + 1, gmask & ~me, 3);
         }
-        // ... and, in the background, everything else to everybody (needed from the end of the level on)
         {
-          B.depend(2, 1);
+          B.depend(2, 3);
           int64_t rb = (int64_t)D.rects.size();
           for (auto &rg : mine)
             if (rg.first < n) D.rects.push_back(RectDesc{base + rg.first + (int64_t)c0 * ld, ld, std::min(rg.second, n) - rg.first, w, kNoTri, 0u, 0});
@@ -609,16 +559,17 @@ int build_schedule(const Problem &P, const Symbolic &S, Schedule &D, int rank, i
             if (rg.second > r0) D.rects.push_back(RectDesc{base + std::max(rg.first, r0) + (int64_t)c0 * ld, ld, rg.second - std::max(rg.first, r0), w, kNoTri, 0u, 0});
           B.push_rects(lvl, phase, rb, wmask & ~me, 0, 0, 0, 2);
         }
-        // trailing update of this rank's rows (K = w); its B operand is the group's pushed rows
-        B.depend(0, 1);
+        B.depend(0, 3);
         B.sync(lvl, phase, SLOT_GROUP, lvl_seq + J + 1, 0, gmask & ~me, 0);
         B.begin_gemm(1);
-        if (n > c1) {
-          const int next_tc = (std::min(RB, n - c1) + 63) / 64;
+        if (has_next) {
+          const int next_tc = (w2 + 63) / 64;
           B.add_problem(base + c1 + (int64_t)c1 * ld, ld, R - c1, n - c1, 1, base + c1 + (int64_t)c0 * ld, base + c1 + (int64_t)c0 * ld, ld, ld, w,
                         c1 / 64, next_tc);
         }
+        B.deep_q = RB / 64;
         B.end_gemm(lvl, phase, false);
+        B.deep_q = 0;
       }
       B.own = nullptr;
       // every rank holds the complete panels of the level once all pushes have landed

@@ -71,19 +71,6 @@ def test_simulated_top_levels_with_the_throughput_path_for_the_rows(monkeypatch,
         assert ok and copy_diff == 0.0, worst
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_simulated_schedule_without_deep_lookahead(monkeypatch, world):
-    """CHOL_DEEP=0: the diagonal block of a top panel is factored after the trailing update of the previous block
-    column (the first version of the owner-computes top), the default runs the diagonal chain one step ahead"""
-    monkeypatch.setenv("CHOL_ROW_BLOCK", "64")
-    monkeypatch.setenv("CHOL_DEEP", "0")
-    grid = (12, 12, 12, 7, 4)
-    for seed in (1, 2):
-        L, copy_diff, _ = sim.factor(grid, world, seed)
-        ok, worst = entrywise_ok(L, oracle_factor(grid))
-        assert ok and copy_diff == 0.0, worst
-
-
 @pytest.mark.parametrize("world", [2, 8])
 def test_simulated_schedule_without_lookahead(monkeypatch, world):
     """CHOL_LOOKAHEAD=0 puts every launch of a rank on one stream in list order: the order of the instrumented
