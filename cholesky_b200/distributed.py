@@ -36,14 +36,24 @@ def make_partitioned(grid=None, files=None, keep_records=False):
     box = [None]
     if rank == 0:
         ch.analyze(keep_records=keep_records)
-        d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-        box[0] = os.path.join(d, f"chol_analysis_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}.bin")
-        ch.save_analysis(box[0])
+        for d in ("/dev/shm", tempfile.gettempdir()):   # (15 MB at 128^3)
+            path = os.path.join(d, f"chol_analysis_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}.bin")
+            try:
+                ch.save_analysis(path)
+                box[0] = path
+                break
+            except Exception:  # noqa: BLE001 -- no room or no such directory: try the next place, else every rank analyses
+                pass
     dist.broadcast_object_list(box, 0)
     if rank != 0:
-        ch.load_analysis(box[0])
+        try:
+            if box[0] is None:
+                raise FileNotFoundError
+            ch.load_analysis(box[0])
+        except Exception:  # noqa: BLE001
+            ch.analyze(keep_records=keep_records)
     dist.barrier()
-    if rank == 0:
+    if rank == 0 and box[0] is not None:
         os.unlink(box[0])
     return ch
 
